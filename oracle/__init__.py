@@ -1,0 +1,5 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the reference hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+package. The product (visco_b200/) never does.
+"""
