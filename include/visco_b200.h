@@ -1,0 +1,128 @@
+/*
+ * visco_b200.h — C ABI of libvisco_b200.so: the B200 (sm_100a) replacement for VISCO's data-parallel hot path.
+ *
+ * The reference has no FFI: its "operator API" for this path is three Python callables
+ *     apply_svd(visdata, decorrelation, compressionrank)      visco/compress_ms.py:322-363
+ *     find_n_decorrelation(singular_values, decorrelation)    visco/compress_ms.py:295-319
+ *     reconstruct_vis(U, S, Vt)                               visco/decompress_ms.py:107-131
+ * invoked once per (baseline, correlation) matrix through dask.delayed (compress_ms.py:610,640,671 and
+ * decompress_ms.py:196). This library is what a ctypes binding behind those names calls; the batched entry
+ * points take every matrix of a dask batch at once (compress_ms.py:571-697, decompress_ms.py:207-213).
+ *
+ * Conventions
+ *   - every function returns an int status (VK_OK == 0); vk_last_error(h) gives a human-readable message.
+ *   - complex64 is interleaved (re, im) float pairs, C order, as numpy stores it.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, 16-byte aligned; the caller owns them.
+ *     "host" entry points take ordinary (ideally pinned) host pointers and do the copies themselves.
+ *   - all device work is enqueued on the handle's stream (vk_set_stream); device entry points are asynchronous
+ *     unless stated otherwise; vk_sync() waits for the stream.
+ *   - one handle per GPU and per host thread; different handles may be used concurrently.
+ *
+ * Layouts (B matrices, each m rows (time) x n columns (channel); r = min(m, n); kmax = padded rank)
+ *   A    [B][m][n]      complex64
+ *   U    [B][m][kmax]   complex64   columns >= ranks[b] are zero
+ *   S    [B][kmax]      float32     entries >= ranks[b] are zero
+ *   Vt   [B][kmax][n]   complex64   rows >= ranks[b] are zero      (the reference calls it Vt / WT)
+ *   ranks[B]            int32
+ *   stats[B][4]         float32     { ||A||_F^2 (sum of all sigma^2), retained energy (sum of kept sigma^2),
+ *                                     Jacobi sweeps used, converged flag (1/0) }
+ */
+#ifndef VISCO_B200_H
+#define VISCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_OK 0
+#define VK_EINVAL 1  /* bad argument (shape, NULL pointer, kmax too small, ...)  -> Python ValueError      */
+#define VK_ENOMEM 2  /* device or host allocation failed                         -> Python MemoryError     */
+#define VK_ECUDA 3   /* a CUDA call or kernel failed                             -> Python RuntimeError    */
+#define VK_ENOCONV 4 /* Jacobi did not converge within max_sweeps (numpy raises LinAlgError here)          */
+#define VK_ENONFINITE 5 /* NaN/Inf in the input (flagged rows NaN-masked by ds.where, compress_ms.py:470)  */
+
+typedef struct vk_context* vk_handle;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------- */
+int vk_create(vk_handle* out, int device);
+int vk_destroy(vk_handle h);
+const char* vk_last_error(vk_handle h);
+const char* vk_version(void);
+/* cudaStream_t passed as void*; NULL = the legacy default stream. */
+int vk_set_stream(vk_handle h, void* cuda_stream);
+int vk_sync(vk_handle h);
+/* options: "jacobi_tol" (relative off-diagonal stop level, default 1e-6), "max_sweeps" (default 30),
+ *          "gram_impl" (0 = auto: tcgen05 where the shape allows, 1 = force SIMT fp32, 2 = force tcgen05),
+ *          "check_finite" (default 1), "check_every" (host convergence poll period in sweeps, default 1),
+ *          "jacobi_bsz" (vectors per block, 0 = auto), "chunk" (matrices per internal pass, 0 = auto),
+ *          "stage_timing" (0/1, see vk_last_stage_ms). */
+int vk_set_option(vk_handle h, const char* key, double value);
+/* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own
+ * workspace when ws == NULL). */
+size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax);
+
+/* ---- the hot path ----------------------------------------------------------------------------------------- */
+/* Replaces apply_svd (compress_ms.py:322-363) for a batch: economy SVD of every A[b], rank choice
+ *   fixed_rank > 0              -> k = min(fixed_rank, r)                     (wins, compress_ms.py:352-353)
+ *   else decorrelation > 0      -> k = find_n_decorrelation(S, decorrelation) (compress_ms.py:295-319, float32)
+ *   else                        -> k = r
+ * and truncated factors. kmax must be >= the largest possible k (fixed_rank, or r in energy/full mode).
+ * Synchronous with respect to `ranks`/`stats` only if the caller syncs; status reflects errors found so far
+ * (convergence / non-finite input are reported by this call because it polls the device while iterating). */
+int vk_compress_batched(vk_handle h, const void* A_dev, int B, int m, int n, int fixed_rank, float decorrelation,
+                        int kmax, void* U_dev, float* S_dev, void* Vt_dev, int32_t* ranks_dev, float* stats_dev,
+                        void* ws_dev, size_t ws_bytes);
+
+/* Replaces reconstruct_vis (decompress_ms.py:107-131) for a batch: out[b] = (U[b] * S[b][None, :]) @ Vt[b],
+ * using the first ranks[b] modes (ranks_dev == NULL -> all kmax modes). out is [B][m][n] complex64. */
+int vk_reconstruct_batched(vk_handle h, const void* U_dev, const float* S_dev, const void* Vt_dev,
+                           const int32_t* ranks_dev, int B, int m, int n, int kmax, void* out_dev);
+
+/* Same two operations with HOST buffers (numpy arrays): H2D copy, compute, D2H copy, synchronous.
+ * These are what the single-matrix Python drop-ins apply_svd / reconstruct_vis call. */
+int vk_compress_host(vk_handle h, const void* A_host, int B, int m, int n, int fixed_rank, float decorrelation,
+                     int kmax, void* U_host, float* S_host, void* Vt_host, int32_t* ranks_host, float* stats_host);
+int vk_reconstruct_host(vk_handle h, const void* U_host, const float* S_host, const void* Vt_host,
+                        const int32_t* ranks_host, int B, int m, int n, int kmax, void* out_host);
+
+/* Replaces find_n_decorrelation (compress_ms.py:295-319) on device: S_dev [B][r] float32 descending. */
+int vk_find_n_decorrelation_batched(vk_handle h, const float* S_dev, int B, int r, float decorrelation,
+                                    int32_t* ranks_dev);
+
+/* ---- stage-level entry points (tests, ncu) ---------------------------------------------------------------- */
+/* Gram product on the smaller side. side 0: W[b][i][t] = sum_v A[t][v] conj(A[i][v])   (r = m, G = A A^H, W = G^T)
+ *                                   side 1: W[b][i][j] = sum_t conj(A[t][j]) A[t][i]   (r = n, G = A^H A, W = G^T)
+ * W is [B][r][r] complex64: row i of W is column i of the Hermitian Gram matrix. impl as "gram_impl". */
+int vk_gram_batched(vk_handle h, const void* A_dev, int B, int m, int n, int side, int impl, void* W_dev);
+/* One-sided cyclic Jacobi on the columns of a Hermitian PSD matrix given as W (above), in place: on return the rows
+ * of W are mutually orthogonal, unnormalised eigenvectors of the Gram matrix (row i = (lambda_i * r / trace) * v_i).
+ * lambda_dev [B][r] receives the eigenvalues sorted descending, info_dev [B][2] = {sweeps, converged}. */
+int vk_eigh_jacobi_batched(vk_handle h, void* W_dev, int B, int r, float* lambda_dev, int32_t* info_dev);
+/* One-sided (Hestenes) Jacobi SVD of small matrices held entirely in shared memory (min(m,n) <= 64 and
+ * min(m,n) * (max(m,n) + min(m,n)) * 8 bytes <= 200 KiB). Full factors, sorted: U [B][m][r], S [B][r], Vt [B][r][n]. */
+int vk_svd_jacobi_small_batched(vk_handle h, const void* A_dev, int B, int m, int n, void* U_dev, float* S_dev,
+                                void* Vt_dev, int32_t* info_dev);
+/* 1 if (m, n) takes the direct small-matrix path inside vk_compress_batched, else 0 (Gram path). */
+int vk_uses_small_path(int m, int n);
+/* 1 if the tcgen05 Gram kernel handles (m, n, side), else 0 (SIMT Gram). */
+int vk_gram_uses_tcgen05(int m, int n, int side);
+
+/* ---- benchmark generator (SURVEY.md section 8d model), on device ------------------------------------------ */
+/* A[b] for b = baseline * ncorr + corr; global baseline index = bl_offset + baseline out of nbl_total. */
+int vk_synth_fill(vk_handle h, void* A_dev, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,
+                  uint64_t seed);
+
+/* number of kernel launches issued through this handle since creation (bench.py's gpu_launches claim) */
+int64_t vk_launch_count(vk_handle h);
+/* elapsed device milliseconds of the stages of the LAST vk_compress_batched call, measured with CUDA events on the
+ * handle's stream: t[0] gram, t[1] jacobi (all sweeps), t[2] select+truncate, t[3] factor formation (U/Vt),
+ * t[4] small-path kernel, t[5] total. Requires option "stage_timing" = 1 (adds event records + one sync). */
+int vk_last_stage_ms(vk_handle h, float* t6);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISCO_B200_H */

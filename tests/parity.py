@@ -1,0 +1,79 @@
+"""Shared parity checks: CUDA path vs the oracle, with the tolerances BASELINE.json's north_star states.
+
+  retained singular values : |S - S_ref| <= 1e-4 * S_ref              (+ 2e-6 * S_ref[0] absolute floor: fp32 noise)
+  reconstruction error     : | ||A - A_hat|| - ||A - A_ref|| | <= 1e-5 * ||A - A_ref||   (+ 2e-6 * ||A|| floor, for
+                             exactly-low-rank inputs whose reference error is itself float32 round-off)
+  chosen rank              : identical, except when the cumulative energy at the smaller of the two ranks lies
+                             within 2e-4 (relative, i.e. a 1e-4 change of one singular value) of the threshold
+Singular vectors are compared through reconstructions and orthonormality only (phase ambiguity).
+"""
+import numpy as np
+
+from oracle import visco_oracle as vo
+
+S_RTOL = 1e-4
+S_FLOOR = 2e-6
+ERR_RTOL = 1e-5
+ERR_FLOOR = 2e-6
+TIE_RTOL = 2e-4
+
+
+def rank_is_acceptable(s_ref, decorrelation, k, k_ref):
+    if k == k_ref:
+        return True
+    s2 = s_ref.astype(np.float32) ** 2
+    total = np.sum(s2)
+    thr = np.float32(decorrelation) ** 2 * total if False else (decorrelation ** 2) * total
+    cum = np.cumsum(s2)
+    lo = min(k, k_ref)
+    hi = max(k, k_ref)
+    # every cumulative energy between the two ranks must sit within the tie band of the threshold
+    band = TIE_RTOL * float(total)
+    return all(abs(float(cum[i - 1]) - float(thr)) <= band for i in range(lo, hi))
+
+
+def check_factors(a, U, S, Vt, k, decorrelation=None, compressionrank=None, label=""):
+    """a: (m, n) complex64; U (m, k), S (k,), Vt (k, n) from the CUDA path. Raises AssertionError with context."""
+    a = np.asarray(a, np.complex64)
+    u_ref, s_ref_full, vt_ref = vo.ref_svd(a)
+    r = len(s_ref_full)
+    if compressionrank:
+        k_ref = min(int(compressionrank), r) if int(compressionrank) <= r else r
+    elif decorrelation:
+        k_ref = vo.ref_find_n_decorrelation(s_ref_full, decorrelation)
+    else:
+        k_ref = r
+    assert U.shape == (a.shape[0], k) and S.shape == (k,) and Vt.shape == (k, a.shape[1]), (label, U.shape, S.shape, Vt.shape)
+    assert U.dtype == np.complex64 and S.dtype == np.float32 and Vt.dtype == np.complex64, label
+    if decorrelation and not compressionrank:
+        assert rank_is_acceptable(s_ref_full, decorrelation, k, k_ref), (label, "rank", k, k_ref)
+    else:
+        assert k == k_ref, (label, "rank", k, k_ref)
+    kk = min(k, k_ref)
+    s1 = float(s_ref_full[0]) if r else 0.0
+    ds = np.abs(S[:kk].astype(np.float64) - s_ref_full[:kk].astype(np.float64))
+    lim = S_RTOL * s_ref_full[:kk].astype(np.float64) + S_FLOOR * s1
+    assert np.all(ds <= lim), (label, "sigma", float((ds / np.maximum(s_ref_full[:kk], 1e-30)).max()))
+    assert np.all(np.diff(S.astype(np.float64)) <= 1e-5 * max(s1, 1e-30)), (label, "S not descending")
+    a64 = a.astype(np.complex128)
+    rec = (U.astype(np.complex128) * S.astype(np.float64)[None, :]) @ Vt.astype(np.complex128)
+    e = np.linalg.norm(a64 - rec)
+    rec_ref = (u_ref[:, :k].astype(np.complex128) * s_ref_full[:k].astype(np.float64)[None, :]) @ vt_ref[:k].astype(np.complex128)
+    e_ref = np.linalg.norm(a64 - rec_ref)
+    na = np.linalg.norm(a64)
+    assert abs(e - e_ref) <= ERR_RTOL * e_ref + ERR_FLOOR * na, (label, "recon err", e, e_ref, (e - e_ref) / max(e_ref, 1e-30))
+    # orthonormal factors (only meaningful for modes above the float32 noise floor)
+    keep = S > 1e-4 * max(s1, 1e-30)
+    if keep.any():
+        Uk, Vk = U[:, keep].astype(np.complex128), Vt[keep].astype(np.complex128)
+        assert np.abs(Uk.conj().T @ Uk - np.eye(Uk.shape[1])).max() < 5e-4, (label, "U orthonormality")
+        assert np.abs(Vk @ Vk.conj().T - np.eye(Vk.shape[0])).max() < 5e-4, (label, "Vt orthonormality")
+    return dict(k=k, k_ref=k_ref, e=e, e_ref=e_ref, smax=float((ds / np.maximum(s_ref_full[:kk], 1e-30)).max()) if kk else 0.0)
+
+
+def check_reconstruction(U, S, Vt, out, label=""):
+    ref = vo.ref_reconstruct_vis(np.asarray(U, np.complex64), np.asarray(S, np.float32), np.asarray(Vt, np.complex64))
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    err = float(np.abs(out - ref).max())
+    assert out.dtype == np.complex64 and out.shape == ref.shape, label
+    assert err <= 2e-5 * scale * max(1.0, np.sqrt(len(S))), (label, "reconstruct", err, scale)

@@ -1,0 +1,270 @@
+"""GPU parity tests: every call goes through the C ABI (libvisco_b200.so); the oracle is only the checker."""
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from visco_b200.engine import get_engine
+    return get_engine(0)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+def test_library_is_the_cuda_one(eng):
+    assert eng.lib.vk_version().decode().endswith("(sm_100a)")
+    assert eng.launch_count >= 0
+
+
+# ---------------------------------------------------------------------------------------- golden fixtures
+def test_golden_full_rank_singular_values(golden, golden_cases):
+    from visco_b200.compress_ms import apply_svd
+    for c in golden_cases:
+        a = golden[f"{c}/A"]
+        U, S, Vt = apply_svd(a)
+        parity.check_factors(a, U, S, Vt, len(S), label=c)
+        s_ref = golden[f"{c}/S"]
+        big = s_ref > 1e-3 * s_ref[0]
+        np.testing.assert_allclose(S[big], s_ref[big], rtol=1e-4, err_msg=c)
+
+
+def test_golden_energy_rule(golden, golden_cases):
+    from visco_b200.compress_ms import apply_svd, find_n_decorrelation
+    decs = golden["decs"]
+    for c in golden_cases:
+        a = golden[f"{c}/A"]
+        s_ref = golden[f"{c}/S"]
+        for d, n_ref in zip(decs, golden[f"{c}/n_dec"]):
+            # the device restatement of find_n_decorrelation on the REFERENCE's singular values: exact match
+            assert find_n_decorrelation(s_ref, float(d)) == int(n_ref), (c, d)
+        for d in (0.9, 0.99):
+            U, S, Vt = apply_svd(a, decorrelation=float(d))
+            parity.check_factors(a, U, S, Vt, len(S), decorrelation=float(d), label=f"{c}@{d}")
+
+
+def test_golden_fixed_rank_and_reconstruction(golden, golden_cases):
+    from visco_b200.compress_ms import apply_svd
+    from visco_b200.decompress_ms import reconstruct_vis
+    for c in golden_cases:
+        a = golden[f"{c}/A"]
+        for k, e_ref in zip(golden[f"{c}/ks"], golden[f"{c}/recon_err"]):
+            U, S, Vt = apply_svd(a, decorrelation=0.9, compressionrank=int(k))     # fixed rank wins
+            assert len(S) == k
+            parity.check_factors(a, U, S, Vt, int(k), compressionrank=int(k), label=f"{c}/k{k}")
+            rec = reconstruct_vis(U, S, Vt)
+            parity.check_reconstruction(U, S, Vt, rec, label=f"{c}/k{k}")
+            e = np.linalg.norm(a.astype(np.complex128) - rec.astype(np.complex128))
+            assert abs(e - e_ref) <= 1e-5 * e_ref + 3e-6 * np.linalg.norm(a), (c, k, e, e_ref)
+            rec2 = reconstruct_vis(U, S.reshape(-1, 1), Vt)                          # (k, 1) form accepted
+            np.testing.assert_array_equal(rec, rec2)
+
+
+def test_cross_reading_reference_factors(golden):
+    """decompress side reads factors the REFERENCE produced (oracle = reference restatement)."""
+    from oracle import visco_oracle as vo
+    from visco_b200.decompress_ms import reconstruct_vis, unstack_vis
+    a = golden["ms_bl12_diag/A"]
+    u, s, vt = vo.ref_apply_svd(a, compressionrank=4)
+    rec = reconstruct_vis(u, s, vt)
+    parity.check_reconstruction(u, s, vt, rec)
+    parts = unstack_vis(rec, 360)
+    assert len(parts) == 2 and parts[0].shape == (360, 16)
+    np.testing.assert_allclose(parts[0], golden["ms_bl12_diag/unstack0"], atol=3e-5 * np.abs(a).max())
+    np.testing.assert_allclose(parts[1], golden["ms_bl12_diag/unstack1"], atol=3e-5 * np.abs(a).max())
+
+
+# ---------------------------------------------------------------------------------------- synthetic cubes
+def _device_cube(eng, torch, nbl, ncorr, m, n, nbl_total=None, bl_offset=0):
+    A = torch.empty((nbl * ncorr, m, n), dtype=torch.complex64, device="cuda:0")
+    eng.synth_fill(A, nbl, ncorr, bl_offset=bl_offset, nbl_total=nbl_total or nbl)
+    return A
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((256, 1024), dict(compressionrank=8)),          # KAT-7 config (C2) shape, Gram path
+    ((128, 512), dict(decorrelation=0.99)),          # energy rule, Gram path, near-full rank on cross hands
+    ((64, 64), dict(decorrelation=0.95)),            # small-matrix regime (C4), direct path
+    ((64, 64), dict(compressionrank=5)),
+    ((360, 16), dict(decorrelation=0.9)),            # sample-MS shape (m > n), direct path
+    ((96, 40), dict(compressionrank=3)),
+    ((200, 72), dict(decorrelation=0.97)),           # m > n on the Gram path (r > 64)
+    ((70, 300), dict()),                             # full rank, odd sizes
+])
+def test_synthetic_cube_against_oracle(eng, torch, shape, kw):
+    m, n = shape
+    nbl, ncorr = 3, 4
+    A = _device_cube(eng, torch, nbl, ncorr, m, n, nbl_total=8, bl_offset=2)
+    U, S, Vt, ranks, stats = eng.compress(A, **kw)
+    out = eng.reconstruct(U, S, Vt, ranks)
+    torch.cuda.synchronize()
+    Ah, Uh, Sh, Vh, rk, st, oh = (x.cpu().numpy() for x in (A, U, S, Vt, ranks, stats, out))
+    assert np.all(st[:, 3] == 1), "Jacobi did not converge"
+    for b in range(nbl * ncorr):
+        k = int(rk[b])
+        parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"{shape}{kw} b={b}", **kw)
+        assert not Uh[b, :, k:].any() and not Sh[b, k:].any() and not Vh[b, k:].any(), "padding must be zero"
+        parity.check_reconstruction(Uh[b, :, :k], Sh[b, :k], Vh[b, :k], oh[b], label=f"recon b={b}")
+        # stats: total and retained energy
+        tot = float(np.sum(np.abs(Ah[b].astype(np.complex128)) ** 2))
+        assert abs(st[b, 0] - tot) <= 1e-4 * tot
+        assert abs(st[b, 1] - float(np.sum(Sh[b, :k].astype(np.float64) ** 2))) <= 1e-4 * tot
+
+
+def test_host_api_matches_device_api(eng, torch):
+    A = _device_cube(eng, torch, 2, 4, 64, 96)
+    U, S, Vt, ranks, _ = eng.compress(A, compressionrank=6)
+    torch.cuda.synchronize()
+    Uh, Sh, Vh, rh, _ = eng.compress_host(A.cpu().numpy(), compressionrank=6)
+    np.testing.assert_array_equal(rh, ranks.cpu().numpy())
+    np.testing.assert_allclose(Sh, S.cpu().numpy(), rtol=1e-6)
+    out_h = eng.reconstruct_host(Uh, Sh, Vh, rh)
+    out_d = eng.reconstruct(U, S, Vt, ranks).cpu().numpy()
+    np.testing.assert_allclose(out_h, out_d, atol=1e-5 * np.abs(out_d).max())
+
+
+# ---------------------------------------------------------------------------------------- stages
+def test_gram_stage_simt(eng, torch):
+    for (m, n) in [(96, 200), (200, 72), (130, 130)]:
+        A = _device_cube(eng, torch, 2, 2, m, n)
+        W = eng.gram(A, impl=1).cpu().numpy()
+        a = A.cpu().numpy().astype(np.complex128)
+        for b in range(A.shape[0]):
+            G = a[b] @ a[b].conj().T if m <= n else a[b].conj().T @ a[b]
+            np.testing.assert_allclose(W[b], G.T, atol=2e-6 * np.abs(G).max())
+
+
+def test_eigh_stage(eng, torch):
+    m, n = 160, 400
+    A = _device_cube(eng, torch, 2, 2, m, n)
+    W = eng.gram(A, impl=1)
+    G = W.cpu().numpy().astype(np.complex128).transpose(0, 2, 1)
+    lam, info = eng.eigh_jacobi(W)
+    lam, info, Wn = lam.cpu().numpy(), info.cpu().numpy(), W.cpu().numpy().astype(np.complex128)
+    assert np.all(info[:, 1] == 1) and np.all(info[:, 0] <= 20)
+    for b in range(G.shape[0]):
+        ev = np.linalg.eigvalsh(G[b])[::-1]
+        np.testing.assert_allclose(lam[b], ev, atol=3e-6 * ev[0])
+        V = Wn[b] / np.linalg.norm(Wn[b], axis=1, keepdims=True)        # rows = eigenvectors
+        assert np.abs(V.conj() @ V.T - np.eye(m)).max() < 1e-4
+        top = np.argsort(-np.linalg.norm(Wn[b], axis=1))[:10]
+        for i in top:
+            v = V[i]
+            rq = np.real(v.conj() @ G[b] @ v)
+            assert np.linalg.norm(G[b] @ v - rq * v) <= 2e-5 * ev[0]
+
+
+def test_small_svd_stage(eng, torch):
+    for (m, n) in [(64, 64), (16, 360), (360, 16), (33, 70), (1, 40), (40, 1), (2, 2)]:
+        A = _device_cube(eng, torch, 2, 2, m, n)
+        U, S, Vt, info = eng.svd_small(A)
+        a = A.cpu().numpy()
+        Uh, Sh, Vh, ih = U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy(), info.cpu().numpy()
+        assert np.all(ih[:, 1] == 1), (m, n, ih)
+        for b in range(a.shape[0]):
+            parity.check_factors(a[b], Uh[b], Sh[b], Vh[b], min(m, n), label=f"small {m}x{n}")
+
+
+# ---------------------------------------------------------------------------------------- edge cases
+def test_empty_batch_and_bad_arguments(eng, torch):
+    from visco_b200.compress_ms import apply_svd, apply_svd_batched
+    from visco_b200.decompress_ms import reconstruct_vis, reconstruct_vis_batched
+    assert apply_svd_batched(np.zeros((0, 8, 8), np.complex64)) == []
+    assert reconstruct_vis_batched([]).shape[0] == 0
+    with pytest.raises(ValueError):
+        apply_svd(np.zeros((4, 4, 4), np.complex64))
+    with pytest.raises(ValueError):
+        reconstruct_vis(np.zeros((4, 2), np.complex64), np.zeros(3, np.float32), np.zeros((2, 5), np.complex64))
+    A = torch.zeros((1, 8, 8), dtype=torch.complex64, device="cuda:0")
+    with pytest.raises(ValueError):
+        eng.compress(A, compressionrank=4, kmax=2)          # kmax too small
+
+
+def test_non_finite_input_is_an_error(eng):
+    from visco_b200.compress_ms import apply_svd
+    a = np.ones((32, 48), np.complex64)
+    a[3, 5] = np.nan
+    with pytest.raises(ValueError):
+        apply_svd(a, compressionrank=2)
+    b = np.ones((128, 256), np.complex64)
+    b[7, 9] = np.inf
+    with pytest.raises(ValueError):
+        apply_svd(b, compressionrank=2)
+
+
+def test_zero_and_rank_deficient_matrices(eng):
+    from visco_b200.compress_ms import apply_svd
+    from visco_b200.decompress_ms import reconstruct_vis
+    z = np.zeros((40, 56), np.complex64)
+    U, S, Vt = apply_svd(z, compressionrank=3)
+    assert S.shape == (3,) and not S.any()
+    assert not reconstruct_vis(U, S, Vt).any()
+    rng = np.random.default_rng(5)
+    for (m, n) in [(48, 64), (150, 300)]:
+        lo = (rng.standard_normal((m, 2)) + 1j * rng.standard_normal((m, 2))) @ \
+             (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n)))
+        lo = lo.astype(np.complex64)
+        U, S, Vt = apply_svd(lo, decorrelation=0.999)
+        assert len(S) <= 2
+        rec = reconstruct_vis(U, S, Vt)
+        U2, S2, Vt2 = apply_svd(lo, compressionrank=2)
+        rec2 = reconstruct_vis(U2, S2, Vt2)
+        assert np.linalg.norm(lo - rec2) <= 1e-5 * np.linalg.norm(lo)
+        assert np.linalg.norm(lo - rec) <= 0.05 * np.linalg.norm(lo)
+
+
+def test_ragged_ranks_in_one_batch(eng):
+    """decompression batches mix ranks (decompress_ms.py:188-199): padded factors + ranks."""
+    from oracle import visco_oracle as vo
+    from visco_b200.decompress_ms import reconstruct_vis_batched
+    rng = np.random.default_rng(11)
+    facs, refs = [], []
+    for k in (1, 7, 3, 12):
+        a = (rng.standard_normal((40, 72)) + 1j * rng.standard_normal((40, 72))).astype(np.complex64)
+        u, s, vt = vo.ref_apply_svd(a, compressionrank=k)
+        facs.append((u, s, vt))
+        refs.append(vo.ref_reconstruct_vis(u, s, vt))
+    out = reconstruct_vis_batched(facs)
+    for b in range(4):
+        np.testing.assert_allclose(out[b], refs[b], atol=3e-5 * np.abs(refs[b]).max())
+
+
+# ---------------------------------------------------------------------------------------- size-independent properties
+def test_properties_at_kat7_config_size(eng, torch):
+    """BASELINE.json configs[1] at full size: 28 baselines x 4 corr x 256 x 1024, k = 8. No oracle at this size
+    beyond a sample; properties: error^2 + retained energy == total energy (projection), idempotence of
+    compress(reconstruct(.)), orthonormal factors."""
+    nbl, ncorr, m, n, k = 28, 4, 256, 1024, 8
+    A = _device_cube(eng, torch, nbl, ncorr, m, n)
+    U, S, Vt, ranks, stats = eng.compress(A, compressionrank=k)
+    out = eng.reconstruct(U, S, Vt, ranks)
+    torch.cuda.synchronize()
+    assert int(ranks.min()) == k and int(ranks.max()) == k
+    st = stats.cpu().numpy().astype(np.float64)
+    assert np.all(st[:, 3] == 1)
+    err2 = (A - out).abs().pow(2).sum(dim=(1, 2)).double().cpu().numpy()
+    tot = A.abs().pow(2).sum(dim=(1, 2)).double().cpu().numpy()
+    kept = S.double().pow(2).sum(dim=1).cpu().numpy()
+    np.testing.assert_allclose(err2 + kept, tot, rtol=2e-5)
+    np.testing.assert_allclose(st[:, 0], tot, rtol=1e-4)
+    I = torch.eye(k, dtype=torch.complex64, device="cuda:0")
+    assert float((U.transpose(1, 2).conj() @ U - I).abs().max()) < 1e-4
+    assert float((Vt @ Vt.transpose(1, 2).conj() - I).abs().max()) < 1e-4
+    # idempotence: compressing the rank-8 reconstruction returns the same singular values and reconstruction
+    U2, S2, Vt2, r2, _ = eng.compress(out, compressionrank=k)
+    out2 = eng.reconstruct(U2, S2, Vt2, r2)
+    torch.cuda.synchronize()
+    assert float((S2 - S).abs().max() / S.max()) < 1e-5
+    assert float((out2 - out).abs().max() / out.abs().max()) < 1e-4
+    # oracle on a sample of the cube
+    Ah = A[[0, 57, 111]].cpu().numpy()
+    for i, b in enumerate((0, 57, 111)):
+        parity.check_factors(Ah[i], U[b].cpu().numpy(), S[b].cpu().numpy(), Vt[b].cpu().numpy(), k,
+                             compressionrank=k, label=f"kat7 b={b}")

@@ -1,0 +1,488 @@
+// C ABI of libvisco_b200.so (see include/visco_b200.h). Orchestrates the stages; no arithmetic here.
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, total;
+};
+
+bool small_path(int m, int n) {
+    const int r = m < n ? m : n;
+    const int L = m < n ? n : m;
+    if (r > 64) return false;
+    return (size_t)(r + (r & 1)) * (size_t)(L + r) * sizeof(float2) + 1024 <= VK_SMEM_BUDGET;
+}
+
+WsLayout ws_layout(int chunk, int m, int n, int kmax) {
+    const int r = m < n ? m : n;
+    const int L = m < n ? n : m;
+    WsLayout w;
+    size_t off = 0;
+    const size_t wbytes = small_path(m, n) ? (size_t)chunk * r * (L + r) * sizeof(float2)
+                                           : (size_t)chunk * r * r * sizeof(float2);
+    w.W = off, off += align_up(wbytes);
+    w.perm = off, off += align_up((size_t)chunk * r * 4);
+    w.inv = off, off += align_up((size_t)chunk * r * 4);
+    w.gscale = off, off += align_up((size_t)chunk * 4);
+    w.sweeps = off, off += align_up((size_t)chunk * 4);
+    w.done = off, off += align_up((size_t)chunk * 4);
+    w.offmax = off, off += align_up((size_t)chunk * 4);
+    w.active = off, off += 256;
+    w.nonfinite = off, off += 256;
+    w.norm2 = off, off += align_up((size_t)chunk * kmax * 4);
+    w.total = off;
+    return w;
+}
+
+int auto_chunk(const vk_context* h, int B, int m, int n) {
+    (void)h;
+    const int r = m < n ? m : n;
+    const int L = m < n ? n : m;
+    const size_t per = small_path(m, n) ? (size_t)r * (L + r) * 8 : (size_t)r * r * 8;
+    // keep the Jacobi working set of one internal pass inside ~half of the 126 MB L2, but never below a few waves
+    size_t c = (64u << 20) / (per ? per : 1);
+    if (c < 32) c = 32;
+    if (c > (size_t)B) c = B;
+    return (int)c;
+}
+
+int ensure(vk_context* h, void** p, size_t* have, size_t need) {
+    if (*have >= need) return VK_OK;
+    if (*p) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    need = align_up(need, 1 << 20);
+    if (cudaMalloc(p, need) != cudaSuccess) {
+        cudaGetLastError();
+        return vk_fail(h, VK_ENOMEM, "cudaMalloc of " + std::to_string(need) + " bytes failed");
+    }
+    *have = need;
+    return VK_OK;
+}
+
+struct StageTimer {
+    vk_context* h;
+    bool on;
+    explicit StageTimer(vk_context* hh) : h(hh), on(hh->stage_timing != 0) {}
+    void mark(int i) {
+        if (on) cudaEventRecord(h->ev[i], h->stream);
+    }
+    void collect(int slot, int i0, int i1) {
+        if (!on) return;
+        float ms = 0.f;
+        cudaEventSynchronize(h->ev[i1]);
+        if (cudaEventElapsedTime(&ms, h->ev[i0], h->ev[i1]) == cudaSuccess) h->stage_ms[slot] += ms;
+    }
+};
+
+int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+                   float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L) {
+    const int r = m < n ? m : n;
+    const int side = m <= n ? 0 : 1;
+    float2* W = reinterpret_cast<float2*>(ws + L.W);
+    int32_t* perm = reinterpret_cast<int32_t*>(ws + L.perm);
+    float* inv = reinterpret_cast<float*>(ws + L.inv);
+    float* gscale = reinterpret_cast<float*>(ws + L.gscale);
+    int32_t* sweeps = reinterpret_cast<int32_t*>(ws + L.sweeps);
+    int32_t* done = reinterpret_cast<int32_t*>(ws + L.done);
+    unsigned* offmax = reinterpret_cast<unsigned*>(ws + L.offmax);
+    int32_t* active = reinterpret_cast<int32_t*>(ws + L.active);
+    int32_t* nonfinite = reinterpret_cast<int32_t*>(ws + L.nonfinite);
+    float* norm2 = reinterpret_cast<float*>(ws + L.norm2);
+    int rc;
+    StageTimer tm(h);
+    VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
+    if (small_path(m, n)) {
+        const int Llong = m < n ? n : m;
+        const JacobiPlan p = vk_jacobi_plan(h, r, Llong, Llong + r);
+        tm.mark(0);
+        if ((rc = vk_launch_pack_small(h, A, B, m, n, W, p.ld, gscale, nonfinite))) return rc;
+        if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active))) return rc;
+        tm.mark(1);
+        if ((rc = vk_launch_select(h, W, B, r, p.ldot, p.ld, gscale, 0, fixed_rank, decorrelation, kmax, perm, inv, S,
+                                   ranks, stats, sweeps, done)))
+            return rc;
+        tm.mark(2);
+        if ((rc = vk_launch_factors_small(h, W, p.ld, B, m, n, kmax, perm, inv, ranks, U, Vt))) return rc;
+        tm.mark(3);
+        tm.collect(4, 0, 1);
+        tm.collect(2, 1, 2);
+        tm.collect(3, 2, 3);
+    } else {
+        const JacobiPlan p = vk_jacobi_plan(h, r, r, r);
+        tm.mark(0);
+        const bool tc = (h->gram_impl == 2) || (h->gram_impl == 0 && vk_gram_tc_supported(m, n, side));
+        if (tc) {
+            if (!vk_gram_tc_supported(m, n, side))
+                return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape");
+            if ((rc = vk_launch_gram_tc(h, A, B, m, n, W))) return rc;
+        } else {
+            if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;
+        }
+        if ((rc = vk_launch_gram_normalise(h, W, B, r, gscale, nonfinite))) return rc;
+        tm.mark(1);
+        if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active))) return rc;
+        tm.mark(2);
+        if ((rc = vk_launch_select(h, W, B, r, p.ldot, p.ld, gscale, 1, fixed_rank, decorrelation, kmax, perm, inv, S,
+                                   ranks, stats, sweeps, done)))
+            return rc;
+        tm.mark(3);
+        if ((rc = vk_launch_factors_gram(h, A, W, B, m, n, side, kmax, perm, inv, ranks, norm2, U, S, Vt, stats)))
+            return rc;
+        tm.mark(4);
+        tm.collect(0, 0, 1);
+        tm.collect(1, 1, 2);
+        tm.collect(2, 2, 3);
+        tm.collect(3, 3, 4);
+    }
+    // poll: non-finite input / non-convergence (one 8-byte copy; the Jacobi loop has usually synchronised already)
+    if (h->check_finite) {
+        VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 1, nonfinite, 4, cudaMemcpyDeviceToHost, h->stream));
+        VK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->h_poll[1]) return vk_fail(h, VK_ENONFINITE, "input contains NaN or Inf");
+    }
+    return VK_OK;
+}
+
+int check_common(vk_context* h, int B, int m, int n, int kmax) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || m < 1 || n < 1 || kmax < 1) return vk_fail(h, VK_EINVAL, "bad shape: need B >= 0, m, n, kmax >= 1");
+    const int r = m < n ? m : n;
+    if (r > VK_MAX_R) return vk_fail(h, VK_EINVAL, "min(m, n) > 2048 is not supported");
+    return VK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vk_version(void) { return "visco_b200 0.1.0 (sm_100a)"; }
+
+int vk_create(vk_handle* out, int device) {
+    if (!out) return VK_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return VK_ECUDA;
+    vk_context* h = new (std::nothrow) vk_context();
+    if (!h) return VK_ENOMEM;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return VK_ECUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        h->num_sms = prop.multiProcessorCount;
+        if (prop.major != 10) {
+            delete h;
+            return VK_ECUDA;  // sm_100a only: no other architecture is built into this library
+        }
+    }
+    if (cudaMallocHost(reinterpret_cast<void**>(&h->h_poll), 64) != cudaSuccess) {
+        delete h;
+        return VK_ENOMEM;
+    }
+    std::memset(h->h_poll, 0, 64);
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    *out = h;
+    return VK_OK;
+}
+
+int vk_destroy(vk_handle h) {
+    if (!h) return VK_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stage) cudaFree(h->stage);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    delete h;
+    return VK_OK;
+}
+
+const char* vk_last_error(vk_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int vk_set_stream(vk_handle h, void* s) {
+    if (!h) return VK_EINVAL;
+    h->stream = reinterpret_cast<cudaStream_t>(s);
+    return VK_OK;
+}
+
+int vk_sync(vk_handle h) {
+    if (!h) return VK_EINVAL;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    VK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VK_OK;
+}
+
+int vk_set_option(vk_handle h, const char* key, double v) {
+    if (!h || !key) return VK_EINVAL;
+    const std::string k(key);
+    if (k == "jacobi_tol")
+        h->jacobi_tol = (float)v;
+    else if (k == "max_sweeps")
+        h->max_sweeps = (int)v;
+    else if (k == "gram_impl")
+        h->gram_impl = (int)v;
+    else if (k == "check_finite")
+        h->check_finite = (int)v;
+    else if (k == "check_every")
+        h->check_every = (int)v;
+    else if (k == "jacobi_bsz")
+        h->jacobi_bsz = (int)v;
+    else if (k == "stage_timing")
+        h->stage_timing = (int)v;
+    else if (k == "chunk")
+        h->chunk = (int)v;
+    else
+        return vk_fail(h, VK_EINVAL, "unknown option " + k);
+    return VK_OK;
+}
+
+size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax) {
+    if (B <= 0 || m < 1 || n < 1 || kmax < 1) return 0;
+    int chunk = (h && h->chunk > 0) ? h->chunk : auto_chunk(h, B, m, n);
+    if (chunk > B) chunk = B;
+    return ws_layout(chunk, m, n, kmax).total;
+}
+
+int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(m, n)) ? 1 : 0; }
+int vk_gram_uses_tcgen05(int m, int n, int side) { return vk_gram_tc_supported(m, n, side) ? 1 : 0; }
+
+int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+                        void* U, float* S, void* Vt, int32_t* ranks, float* stats, void* ws, size_t ws_bytes) {
+    int rc = check_common(h, B, m, n, kmax);
+    if (rc) return rc;
+    if (B == 0) return VK_OK;
+    if (!A || !U || !S || !Vt || !ranks || !stats) return vk_fail(h, VK_EINVAL, "null buffer");
+    const int r = m < n ? m : n;
+    const int need_k = fixed_rank > 0 ? (fixed_rank < r ? fixed_rank : r) : r;
+    if (kmax < need_k) return vk_fail(h, VK_EINVAL, "kmax smaller than the largest possible rank");
+    if (kmax > r) return vk_fail(h, VK_EINVAL, "kmax larger than min(m, n)");
+    if (decorrelation < 0.f || !(decorrelation == decorrelation))
+        return vk_fail(h, VK_EINVAL, "decorrelation must be >= 0");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n);
+    if (chunk > B) chunk = B;
+    const WsLayout L = ws_layout(chunk, m, n, kmax);
+    unsigned char* wsp = static_cast<unsigned char*>(ws);
+    if (!wsp) {
+        if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total))) return rc;
+        wsp = static_cast<unsigned char*>(h->ws);
+    } else if (ws_bytes < L.total) {
+        return vk_fail(h, VK_EINVAL, "workspace too small: need " + std::to_string(L.total) + " bytes");
+    }
+    for (int i = 0; i < 6; ++i) h->stage_ms[i] = 0.f;
+    cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
+    if (h->stage_timing) cudaEventRecord(e0, h->stream);
+    const float2* Ap = static_cast<const float2*>(A);
+    float2* Up = static_cast<float2*>(U);
+    float2* Vp = static_cast<float2*>(Vt);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (B - b0) < chunk ? (B - b0) : chunk;
+        rc = compress_chunk(h, Ap + (size_t)b0 * m * n, nb, m, n, fixed_rank, decorrelation, kmax,
+                            Up + (size_t)b0 * m * kmax, S + (size_t)b0 * kmax, Vp + (size_t)b0 * kmax * n, ranks + b0,
+                            stats + (size_t)b0 * 4, wsp, L);
+        if (rc) return rc;
+    }
+    if (h->stage_timing) {
+        cudaEventRecord(e1, h->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&h->stage_ms[5], e0, e1);
+    }
+    return VK_OK;
+}
+
+int vk_reconstruct_batched(vk_handle h, const void* U, const float* S, const void* Vt, const int32_t* ranks, int B,
+                           int m, int n, int kmax, void* out) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || m < 1 || n < 1 || kmax < 1) return vk_fail(h, VK_EINVAL, "bad shape: need B >= 0, m, n, kmax >= 1");
+    if (B == 0) return VK_OK;
+    if (!U || !S || !Vt || !out) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    return vk_launch_reconstruct(h, static_cast<const float2*>(U), S, static_cast<const float2*>(Vt), ranks, B, m, n,
+                                 kmax, static_cast<float2*>(out));
+}
+
+int vk_find_n_decorrelation_batched(vk_handle h, const float* S, int B, int r, float decorrelation, int32_t* ranks) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || r < 1 || !S || !ranks) return vk_fail(h, VK_EINVAL, "bad argument");
+    if (B == 0) return VK_OK;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    return vk_launch_find_n(h, S, B, r, decorrelation, ranks);
+}
+
+int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+                     void* U, float* S, void* Vt, int32_t* ranks, float* stats) {
+    int rc = check_common(h, B, m, n, kmax);
+    if (rc) return rc;
+    if (B == 0) return VK_OK;
+    if (!A || !U || !S || !Vt || !ranks || !stats) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    const size_t bA = align_up((size_t)B * m * n * 8), bU = align_up((size_t)B * m * kmax * 8),
+                 bS = align_up((size_t)B * kmax * 4), bV = align_up((size_t)B * kmax * n * 8),
+                 bR = align_up((size_t)B * 4), bT = align_up((size_t)B * 16);
+    if ((rc = ensure(h, &h->stage, &h->stage_bytes, bA + bU + bS + bV + bR + bT))) return rc;
+    unsigned char* p = static_cast<unsigned char*>(h->stage);
+    void* dA = p;
+    void* dU = p + bA;
+    float* dS = reinterpret_cast<float*>(p + bA + bU);
+    void* dV = p + bA + bU + bS;
+    int32_t* dR = reinterpret_cast<int32_t*>(p + bA + bU + bS + bV);
+    float* dT = reinterpret_cast<float*>(p + bA + bU + bS + bV + bR);
+    VK_CUDA(h, cudaMemcpyAsync(dA, A, (size_t)B * m * n * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = vk_compress_batched(h, dA, B, m, n, fixed_rank, decorrelation, kmax, dU, dS, dV, dR, dT, nullptr, 0);
+    if (rc) return rc;
+    VK_CUDA(h, cudaMemcpyAsync(U, dU, (size_t)B * m * kmax * 8, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(S, dS, (size_t)B * kmax * 4, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(Vt, dV, (size_t)B * kmax * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(ranks, dR, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(stats, dT, (size_t)B * 16, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b)
+        if (stats[4 * b + 3] == 0.f)
+            return vk_fail(h, VK_ENOCONV, "Jacobi did not converge for matrix " + std::to_string(b));
+    return VK_OK;
+}
+
+int vk_reconstruct_host(vk_handle h, const void* U, const float* S, const void* Vt, const int32_t* ranks, int B, int m,
+                        int n, int kmax, void* out) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || m < 1 || n < 1 || kmax < 1) return vk_fail(h, VK_EINVAL, "bad shape: need B >= 0, m, n, kmax >= 1");
+    if (B == 0) return VK_OK;
+    if (!U || !S || !Vt || !out) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    const size_t bO = align_up((size_t)B * m * n * 8), bU = align_up((size_t)B * m * kmax * 8),
+                 bS = align_up((size_t)B * kmax * 4), bV = align_up((size_t)B * kmax * n * 8),
+                 bR = align_up((size_t)B * 4);
+    if ((rc = ensure(h, &h->stage, &h->stage_bytes, bO + bU + bS + bV + bR))) return rc;
+    unsigned char* p = static_cast<unsigned char*>(h->stage);
+    void* dO = p;
+    void* dU = p + bO;
+    float* dS = reinterpret_cast<float*>(p + bO + bU);
+    void* dV = p + bO + bU + bS;
+    int32_t* dR = reinterpret_cast<int32_t*>(p + bO + bU + bS + bV);
+    VK_CUDA(h, cudaMemcpyAsync(dU, U, (size_t)B * m * kmax * 8, cudaMemcpyHostToDevice, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(dS, S, (size_t)B * kmax * 4, cudaMemcpyHostToDevice, h->stream));
+    VK_CUDA(h, cudaMemcpyAsync(dV, Vt, (size_t)B * kmax * n * 8, cudaMemcpyHostToDevice, h->stream));
+    if (ranks) VK_CUDA(h, cudaMemcpyAsync(dR, ranks, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+    rc = vk_reconstruct_batched(h, dU, dS, dV, ranks ? dR : nullptr, B, m, n, kmax, dO);
+    if (rc) return rc;
+    VK_CUDA(h, cudaMemcpyAsync(out, dO, (size_t)B * m * n * 8, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VK_OK;
+}
+
+int vk_gram_batched(vk_handle h, const void* A, int B, int m, int n, int side, int impl, void* W) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || m < 1 || n < 1 || (side != 0 && side != 1) || !A || !W) return vk_fail(h, VK_EINVAL, "bad argument");
+    if (B == 0) return VK_OK;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    const bool tc = impl == 2 || (impl == 0 && vk_gram_tc_supported(m, n, side));
+    if (tc) {
+        if (!vk_gram_tc_supported(m, n, side)) return vk_fail(h, VK_EINVAL, "tcgen05 Gram does not support this shape");
+        return vk_launch_gram_tc(h, static_cast<const float2*>(A), B, m, n, static_cast<float2*>(W));
+    }
+    return vk_launch_gram_simt(h, static_cast<const float2*>(A), B, m, n, side, static_cast<float2*>(W));
+}
+
+int vk_eigh_jacobi_batched(vk_handle h, void* W, int B, int r, float* lambda, int32_t* info) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || r < 1 || r > VK_MAX_R || !W || !lambda || !info) return vk_fail(h, VK_EINVAL, "bad argument");
+    if (B == 0) return VK_OK;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    // bookkeeping scratch only (the caller owns W)
+    size_t off = 0;
+    const size_t o_perm = off; off += align_up((size_t)B * r * 4);
+    const size_t o_inv = off; off += align_up((size_t)B * r * 4);
+    const size_t o_g = off; off += align_up((size_t)B * 4);
+    const size_t o_sw = off; off += align_up((size_t)B * 4);
+    const size_t o_dn = off; off += align_up((size_t)B * 4);
+    const size_t o_om = off; off += align_up((size_t)B * 4);
+    const size_t o_rk = off; off += align_up((size_t)B * 4);
+    const size_t o_st = off; off += align_up((size_t)B * 16);
+    const size_t o_ac = off; off += 256;
+    const size_t o_nf = off; off += 256;
+    if ((rc = ensure(h, &h->ws, &h->ws_bytes, off))) return rc;
+    unsigned char* ws = static_cast<unsigned char*>(h->ws);
+    int32_t* perm = reinterpret_cast<int32_t*>(ws + o_perm);
+    float* inv = reinterpret_cast<float*>(ws + o_inv);
+    float* gscale = reinterpret_cast<float*>(ws + o_g);
+    int32_t* sweeps = reinterpret_cast<int32_t*>(ws + o_sw);
+    int32_t* done = reinterpret_cast<int32_t*>(ws + o_dn);
+    unsigned* offmax = reinterpret_cast<unsigned*>(ws + o_om);
+    int32_t* ranks = reinterpret_cast<int32_t*>(ws + o_rk);
+    float* stats = reinterpret_cast<float*>(ws + o_st);
+    int32_t* active = reinterpret_cast<int32_t*>(ws + o_ac);
+    int32_t* nonfinite = reinterpret_cast<int32_t*>(ws + o_nf);
+    float2* Wp = static_cast<float2*>(W);
+    VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
+    if ((rc = vk_launch_gram_normalise(h, Wp, B, r, gscale, nonfinite))) return rc;
+    const JacobiPlan p = vk_jacobi_plan(h, r, r, r);
+    if ((rc = vk_launch_jacobi(h, Wp, B, p, sweeps, done, offmax, active))) return rc;
+    // mode 2: report the eigenvalues themselves (norm * trace scale), sorted descending
+    if ((rc = vk_launch_select(h, Wp, B, r, r, r, gscale, 2, 0, 0.f, r, perm, inv, lambda, ranks, stats, sweeps, done)))
+        return rc;
+    return vk_launch_pack_info(h, sweeps, done, B, info);
+}
+
+int vk_svd_jacobi_small_batched(vk_handle h, const void* A, int B, int m, int n, void* U, float* S, void* Vt,
+                                int32_t* info) {
+    if (!h) return VK_EINVAL;
+    if (B < 0 || m < 1 || n < 1 || !A || !U || !S || !Vt) return vk_fail(h, VK_EINVAL, "bad argument");
+    if (!small_path(m, n)) return vk_fail(h, VK_EINVAL, "shape is not eligible for the small-matrix path");
+    if (B == 0) return VK_OK;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    const int r = m < n ? m : n;
+    int rc;
+    // ranks + stats scratch live behind the regular workspace
+    const WsLayout L = ws_layout(B, m, n, r);
+    const size_t extra = align_up((size_t)B * 4) + align_up((size_t)B * 16);
+    if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total + extra))) return rc;
+    unsigned char* ws = static_cast<unsigned char*>(h->ws);
+    int32_t* ranks = reinterpret_cast<int32_t*>(ws + L.total);
+    float* stats = reinterpret_cast<float*>(ws + L.total + align_up((size_t)B * 4));
+    const int save = h->check_finite;
+    h->check_finite = 0;
+    rc = compress_chunk(h, static_cast<const float2*>(A), B, m, n, 0, 0.f, r, static_cast<float2*>(U), S,
+                        static_cast<float2*>(Vt), ranks, stats, ws, L);
+    h->check_finite = save;
+    if (rc) return rc;
+    if (info) {
+        const int32_t* sweeps = reinterpret_cast<const int32_t*>(ws + L.sweeps);
+        const int32_t* done = reinterpret_cast<const int32_t*>(ws + L.done);
+        if ((rc = vk_launch_pack_info(h, sweeps, done, B, info))) return rc;
+    }
+    return VK_OK;
+}
+
+int vk_synth_fill(vk_handle h, void* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,
+                  uint64_t seed) {
+    if (!h) return VK_EINVAL;
+    if (!A || nbl_local < 0 || ncorr < 1 || m < 1 || n < 1 || nbl_total < 1) return vk_fail(h, VK_EINVAL, "bad argument");
+    if (nbl_local == 0) return VK_OK;
+    VK_CUDA(h, cudaSetDevice(h->device));
+    return vk_launch_synth(h, static_cast<float2*>(A), nbl_local, ncorr, m, n, bl_offset, nbl_total, seed);
+}
+
+int64_t vk_launch_count(vk_handle h) { return h ? h->launches : 0; }
+
+int vk_last_stage_ms(vk_handle h, float* t6) {
+    if (!h || !t6) return VK_EINVAL;
+    for (int i = 0; i < 6; ++i) t6[i] = h->stage_ms[i];
+    return VK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// Shared declarations for libvisco_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/visco_b200.h"
+
+#define VK_SMEM_BUDGET (200 * 1024)  // dynamic shared memory we allow one CTA to ask for
+#define VK_MAX_R 2048                // largest min(m, n) the selection kernel sorts
+
+struct vk_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    void* ws = nullptr;  // grow-only device workspace owned by the handle
+    size_t ws_bytes = 0;
+    void* stage = nullptr;  // grow-only device staging for the *_host entry points
+    size_t stage_bytes = 0;
+    int32_t* h_poll = nullptr;  // pinned host words the convergence loop copies into
+    int64_t launches = 0;
+    int num_sms = 148;
+    // options
+    float jacobi_tol = 1e-6f;
+    int max_sweeps = 30;
+    int gram_impl = 0;
+    int check_finite = 1;
+    int check_every = 1;
+    int jacobi_bsz = 0;  // 0 = auto
+    int stage_timing = 0;
+    int chunk = 0;  // matrices per internal pass, 0 = auto
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+#define VK_CUDA(h, call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            (h)->err = std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                       std::to_string(__LINE__) + ")";                                                     \
+            return VK_ECUDA;                                                                               \
+        }                                                                                                  \
+    } while (0)
+
+#define VK_LAUNCH_CHECK(h)                  \
+    do {                                    \
+        (h)->launches++;                    \
+        VK_CUDA(h, cudaPeekAtLastError()); \
+    } while (0)
+
+static inline int vk_fail(vk_context* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+// ---- small device helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// acc += a * b
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.x = fmaf(-a.y, b.y, acc.x);
+    acc.y = fmaf(a.x, b.y, acc.y);
+    acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---- stage launchers (defined in the .cu files) -------------------------------------------------------------
+// Layout of the "vector workspace" W used by the eigensolver / small SVD: [B][r][ld] complex64, vector i contiguous.
+struct JacobiPlan {
+    int r;      // number of vectors
+    int ldot;   // leading entries that enter the inner products
+    int ltot;   // entries that are rotated (ltot - ldot trailing entries carry the accumulated rotations)
+    int ld;     // stride between vectors (>= ltot)
+    int bsz;    // vectors per block (= warps per CTA)
+    int nb;     // number of blocks (even)
+    size_t smem;
+};
+JacobiPlan vk_jacobi_plan(const vk_context* h, int r, int ldot, int ltot);
+
+// W in/out; offmax/done/sweeps are per-matrix device arrays of length B (int32 / float bits), active is 1 int.
+int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32_t* sweeps_dev, int32_t* done_dev,
+                     unsigned* offmax_dev, int32_t* active_dev);
+
+int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int side, float2* W);
+int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float2* W);
+bool vk_gram_tc_supported(int m, int n, int side);
+
+// scale[b] = r / trace(W[b]) applied in place; gscale_dev[b] = trace/r ; nonfinite_dev[0] |= 1 when trace is NaN/Inf
+int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev);
+
+// small path: build [B][r][ld] vectors (rows of A, or columns when m > n) followed by an r x r identity
+int vk_launch_pack_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, int ld, float* gscale_dev,
+                         int32_t* nonfinite_dev);
+
+// norms of the vectors, sort, sigma, rank choice. mode_gram: sigma = sqrt(norm * gscale) else sigma = norm * gscale
+int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int ld, const float* gscale_dev,
+                     int mode_gram, int fixed_rank, float decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
+                     float* S_dev, int32_t* ranks_dev, float* stats_dev, const int32_t* sweeps_dev,
+                     const int32_t* done_dev);
+int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info);
+int vk_launch_find_n(vk_context* h, const float* S, int B, int r, float decorrelation, int32_t* ranks);
+
+// factor formation
+int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int B, int m, int n, int side, int kmax,
+                           const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float* norm2_dev,
+                           float2* U, float* S, float2* Vt, float* stats_dev);
+int vk_launch_factors_small(vk_context* h, const float2* W, int ld, int B, int m, int n, int kmax,
+                            const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float2* U,
+                            float2* Vt);
+int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
+                          int m, int n, int kmax, float2* out);
+int vk_launch_synth(vk_context* h, float2* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,
+                    uint64_t seed);

@@ -1,0 +1,660 @@
+// SIMT stages of the hot path (sm_100a): Gram product for shapes the tcgen05 kernel does not take, Gram
+// normalisation, small-matrix packing, singular-value selection / rank truncation, factor formation, rank-k
+// reconstruction, and the benchmark generator. Reference call sites are cited at each launcher.
+#include "cgemm.cuh"
+
+namespace {
+
+// =================================================================================================================
+// Gram product (SIMT)                                    reference: implicit in np.linalg.svd, compress_ms.py:350
+// =================================================================================================================
+struct GramOp0 {  // W[i][t] = sum_v conj(A[i][v]) * A[t][v]          (r = m)
+    const float2* A;
+    float2* W;
+    int m, n;
+    static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
+    static constexpr int REDUCE = 0;
+    __device__ int M(int) const { return m; }
+    __device__ int N(int) const { return m; }
+    __device__ int K(int) const { return n; }
+    __host__ __device__ int Mfill() const { return m; }
+    __host__ __device__ int Nfill() const { return m; }
+    __device__ float2 loadA(int b, int i, int k) const {
+        const float2 v = A[((size_t)b * m + i) * n + k];
+        return make_float2(v.x, -v.y);
+    }
+    __device__ float2 loadB(int b, int k, int j) const { return A[((size_t)b * m + j) * n + k]; }
+    __device__ void store(int b, int i, int j, float2 v) const { W[((size_t)b * m + i) * m + j] = v; }
+    __device__ void reduce_add(int, int, float) const {}
+};
+struct GramOp1 {  // W[i][j] = sum_t A[t][i] * conj(A[t][j])          (r = n)
+    const float2* A;
+    float2* W;
+    int m, n;
+    static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
+    static constexpr int REDUCE = 0;
+    __device__ int M(int) const { return n; }
+    __device__ int N(int) const { return n; }
+    __device__ int K(int) const { return m; }
+    __host__ __device__ int Mfill() const { return n; }
+    __host__ __device__ int Nfill() const { return n; }
+    __device__ float2 loadA(int b, int i, int k) const { return A[((size_t)b * m + k) * n + i]; }
+    __device__ float2 loadB(int b, int k, int j) const {
+        const float2 v = A[((size_t)b * m + k) * n + j];
+        return make_float2(v.x, -v.y);
+    }
+    __device__ void store(int b, int i, int j, float2 v) const { W[((size_t)b * n + i) * n + j] = v; }
+    __device__ void reduce_add(int, int, float) const {}
+};
+
+// scale W[b] so that trace == r; gscale[b] = trace / r. One CTA per matrix.
+__global__ void __launch_bounds__(256) gram_normalise_kernel(float2* __restrict__ W, int r, float* __restrict__ gscale,
+                                                             int32_t* __restrict__ nonfinite) {
+    __shared__ float part[8];
+    __shared__ float sc;
+    const int b = blockIdx.x;
+    float2* Wb = W + (size_t)b * r * r;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < r; i += blockDim.x) s += Wb[(size_t)i * r + i].x;
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tr = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tr += part[w];
+        float g = tr / (float)r;
+        if (!isfinite(g)) {
+            atomicOr(nonfinite, 1);
+            g = 1.f;
+        }
+        if (!(g > 0.f)) g = 1.f;  // all-zero matrix: leave it alone
+        gscale[b] = g;
+        sc = 1.f / g;
+    }
+    __syncthreads();
+    const float f = sc;
+    const size_t tot = (size_t)r * r;
+    for (size_t e = threadIdx.x; e < tot; e += blockDim.x) {
+        float2 v = Wb[e];
+        v.x *= f;
+        v.y *= f;
+        Wb[e] = v;
+    }
+}
+
+// Small path: vectors = rows of A (m <= n) or columns of A (m > n), normalised to unit rms norm, followed by e_i.
+__global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restrict__ A, int m, int n,
+                                                         float2* __restrict__ W, int ld, float* __restrict__ gscale,
+                                                         int32_t* __restrict__ nonfinite) {
+    __shared__ float part[8];
+    __shared__ float sc;
+    const int b = blockIdx.x;
+    const float2* Ab = A + (size_t)b * m * n;
+    const int r = m <= n ? m : n;
+    const int L = m <= n ? n : m;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+        const float2 v = Ab[e];
+        s = fmaf(v.x, v.x, fmaf(v.y, v.y, s));
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+        float g = sqrtf(tot / (float)r);
+        if (!isfinite(g)) {
+            atomicOr(nonfinite, 1);
+            g = 1.f;
+        }
+        if (!(g > 0.f)) g = 1.f;
+        gscale[b] = g;
+        sc = 1.f / g;
+    }
+    __syncthreads();
+    const float f = sc;
+    float2* Wb = W + (size_t)b * r * ld;
+    if (m <= n) {
+        for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+            const int i = e / n, x = e - i * n;
+            float2 v = Ab[e];
+            v.x *= f;
+            v.y *= f;
+            Wb[(size_t)i * ld + x] = v;
+        }
+    } else {
+        // vector j = column j of A; read A coalesced, scattered (small) writes
+        for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+            const int t = e / n, j = e - t * n;
+            float2 v = Ab[e];
+            v.x *= f;
+            v.y *= f;
+            Wb[(size_t)j * ld + t] = v;
+        }
+    }
+    for (int e = threadIdx.x; e < r * r; e += blockDim.x) {
+        const int i = e / r, j = e - i * r;
+        Wb[(size_t)i * ld + L + j] = make_float2(i == j ? 1.f : 0.f, 0.f);
+    }
+}
+
+// =================================================================================================================
+// Selection: norms -> sort -> sigma -> rank              reference: compress_ms.py:295-319 (energy rule, float32),
+//                                                                   compress_ms.py:352-361 (precedence, slicing)
+// =================================================================================================================
+__device__ __forceinline__ int energy_rank(const float* sig, int r, float decorrelation) {
+    // total = sum(S^2) ; threshold = float32(dec^2) * total ; cumulative = cumsum(S^2) ; argmax(cum >= thr) + 1
+    double tot = 0.0;
+    for (int c = 0; c < r; ++c) tot += (double)(sig[c] * sig[c]);
+    const float total = (float)tot;
+    const float thr = (float)((double)decorrelation * (double)decorrelation) * total;
+    float cum = 0.f;
+    for (int c = 0; c < r; ++c) {
+        cum += sig[c] * sig[c];
+        if (cum >= thr) return c + 1;
+    }
+    return 1;  // argmax of an all-False array is 0
+}
+
+__global__ void __launch_bounds__(256)
+select_kernel(const float2* __restrict__ W, int r, int ldot, int ld, const float* __restrict__ gscale, int mode_gram,
+              int fixed_rank, float decorrelation, int kmax, int32_t* __restrict__ perm, float* __restrict__ inv,
+              float* __restrict__ S, int32_t* __restrict__ ranks, float* __restrict__ stats,
+              const int32_t* __restrict__ sweeps, const int32_t* __restrict__ done) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int P = 1;
+    while (P < r) P <<= 1;
+    float* key = reinterpret_cast<float*>(smem_raw);  // [P]
+    int* idx = reinterpret_cast<int*>(key + P);       // [P]
+    float* sig = reinterpret_cast<float*>(idx + P);   // [P]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const float2* Wb = W + (size_t)b * r * ld;
+    for (int i = warp; i < P; i += nwarps) {
+        float s = -1.f;
+        if (i < r) {
+            const float2* v = Wb + (size_t)i * ld;
+            float acc = 0.f;
+            for (int t = lane; t < ldot; t += 32) {
+                const float2 x = v[t];
+                acc = fmaf(x.x, x.x, fmaf(x.y, x.y, acc));
+            }
+            acc = warp_sum(acc);
+            s = sqrtf(acc);
+            if (!(s >= 0.f)) s = 0.f;  // NaN -> 0 (flagged elsewhere)
+        }
+        if (lane == 0) {
+            key[i] = s;
+            idx[i] = i;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending by key (ties: lower index first)
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P; t += blockDim.x) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const bool desc = ((t & k) == 0);
+                    const float kt = key[t], kp = key[p];
+                    const int it = idx[t], ip = idx[p];
+                    const bool t_before_p = (kt > kp) || (kt == kp && it < ip);
+                    if (desc ? !t_before_p : t_before_p) {
+                        key[t] = kp;
+                        key[p] = kt;
+                        idx[t] = ip;
+                        idx[p] = it;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const float g = gscale[b];
+    for (int c = threadIdx.x; c < r; c += blockDim.x) {
+        const float nv = key[c];
+        sig[c] = (mode_gram == 1) ? sqrtf(nv * g) : nv * g;
+    }
+    __syncthreads();
+    __shared__ int k_sh;
+    if (threadIdx.x == 0) {
+        int k;
+        if (fixed_rank > 0)
+            k = fixed_rank < r ? fixed_rank : r;
+        else if (decorrelation > 0.f)
+            k = energy_rank(sig, r, decorrelation);
+        else
+            k = r;
+        if (k > kmax) k = kmax;
+        k_sh = k;
+        ranks[b] = k;
+        double tot = 0.0, kept = 0.0;
+        for (int c = 0; c < r; ++c) {
+            const double e = (double)sig[c] * (double)sig[c];
+            tot += e;
+            if (c < k) kept += e;
+        }
+        stats[4 * b + 0] = (float)tot;
+        stats[4 * b + 1] = (float)kept;
+        stats[4 * b + 2] = (float)sweeps[b];
+        stats[4 * b + 3] = (float)done[b];
+    }
+    __syncthreads();
+    const int k = k_sh;
+    for (int c = threadIdx.x; c < r; c += blockDim.x) {
+        perm[(size_t)b * r + c] = idx[c];
+        const float nv = key[c];
+        inv[(size_t)b * r + c] = nv > 0.f ? 1.f / nv : 0.f;
+    }
+    for (int c = threadIdx.x; c < kmax; c += blockDim.x) S[(size_t)b * kmax + c] = (c < k) ? sig[c] : 0.f;
+}
+
+__global__ void pack_info_kernel(const int32_t* __restrict__ sweeps, const int32_t* __restrict__ done, int B,
+                                 int32_t* __restrict__ info) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        info[2 * b] = sweeps[b];
+        info[2 * b + 1] = done[b];
+    }
+}
+
+__global__ void find_n_kernel(const float* __restrict__ S, int B, int r, float decorrelation,
+                              int32_t* __restrict__ ranks) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ranks[b] = energy_rank(S + (size_t)b * r, r, decorrelation);
+}
+
+// =================================================================================================================
+// Factor formation                                        reference: U[:, :n], S[:n], Vt[:n, :] compress_ms.py:359-361
+// =================================================================================================================
+// dst[b][c][x] = f(W[b][perm[c]][off + x]) * (scaled ? inv[c] : 1), zero for c >= rank.   x < len, c < kmax
+__global__ void __launch_bounds__(256)
+rows_from_vectors_kernel(const float2* __restrict__ W, int r, int ld, int off, int len, int kmax,
+                         const int32_t* __restrict__ perm, const float* __restrict__ inv,
+                         const int32_t* __restrict__ ranks, int conj, int scaled, float2* __restrict__ dst) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    float2* d = dst + ((size_t)b * kmax + c) * len;
+    if (c >= ranks[b]) {
+        for (int x = threadIdx.x; x < len; x += blockDim.x) d[x] = make_float2(0.f, 0.f);
+        return;
+    }
+    const int p = perm[(size_t)b * r + c];
+    const float f = scaled ? inv[(size_t)b * r + c] : 1.f;
+    const float fi = conj ? -f : f;
+    const float2* src = W + ((size_t)b * r + p) * ld + off;
+    for (int x = threadIdx.x; x < len; x += blockDim.x) {
+        const float2 v = src[x];
+        d[x] = make_float2(v.x * f, v.y * fi);
+    }
+}
+// dst[b][t][c] = f(W[b][perm[c]][off + t]) * (scaled ? inv[c] : 1), zero for c >= rank.   t < len, c < kmax
+__global__ void __launch_bounds__(256)
+cols_from_vectors_kernel(const float2* __restrict__ W, int r, int ld, int off, int len, int kmax,
+                         const int32_t* __restrict__ perm, const float* __restrict__ inv,
+                         const int32_t* __restrict__ ranks, int conj, int scaled, float2* __restrict__ dst) {
+    __shared__ float2 tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps
+    const int k = ranks[b];
+    for (int cc = ty; cc < 32; cc += 8) {
+        const int c = c0 + cc, t = t0 + tx;
+        float2 v = make_float2(0.f, 0.f);
+        if (c < k && t < len) {
+            const int p = perm[(size_t)b * r + c];
+            const float f = scaled ? inv[(size_t)b * r + c] : 1.f;
+            const float2 s = W[((size_t)b * r + p) * ld + off + t];
+            v = make_float2(s.x * f, conj ? -s.y * f : s.y * f);
+        }
+        tile[cc][tx] = v;
+    }
+    __syncthreads();
+    for (int tt = ty; tt < 32; tt += 8) {
+        const int t = t0 + tt, c = c0 + tx;
+        if (t < len && c < kmax) dst[((size_t)b * len + t) * kmax + c] = tile[tx][tt];
+    }
+}
+
+struct FormVOp {  // Vt[c][v] = sum_t conj(W[perm c][t]) inv[c] * A[t][v]            (wide, r = m)
+    const float2* A;
+    const float2* W;
+    const int32_t* perm;
+    const float* inv;
+    const int32_t* ranks;
+    float2* Vt;
+    float* norm2;
+    int m, n, kmax;
+    static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
+    static constexpr int REDUCE = 1;
+    __device__ int M(int b) const { return ranks[b]; }
+    __device__ int N(int) const { return n; }
+    __device__ int K(int) const { return m; }
+    __host__ __device__ int Mfill() const { return kmax; }
+    __host__ __device__ int Nfill() const { return n; }
+    __device__ float2 loadA(int b, int c, int t) const {
+        const int p = perm[(size_t)b * m + c];
+        const float f = inv[(size_t)b * m + c];
+        const float2 v = W[((size_t)b * m + p) * m + t];
+        return make_float2(v.x * f, -v.y * f);
+    }
+    __device__ float2 loadB(int b, int t, int j) const { return A[((size_t)b * m + t) * n + j]; }
+    __device__ void store(int b, int c, int j, float2 v) const { Vt[((size_t)b * kmax + c) * n + j] = v; }
+    __device__ void reduce_add(int b, int c, float v) const { atomicAdd(&norm2[(size_t)b * kmax + c], v); }
+};
+struct FormUOp {  // U[t][c] = sum_j A[t][j] * W[perm c][j] inv[c]                    (tall, r = n)
+    const float2* A;
+    const float2* W;
+    const int32_t* perm;
+    const float* inv;
+    const int32_t* ranks;
+    float2* U;
+    float* norm2;
+    int m, n, kmax;
+    static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
+    static constexpr int REDUCE = 2;
+    __device__ int M(int) const { return m; }
+    __device__ int N(int b) const { return ranks[b]; }
+    __device__ int K(int) const { return n; }
+    __host__ __device__ int Mfill() const { return m; }
+    __host__ __device__ int Nfill() const { return kmax; }
+    __device__ float2 loadA(int b, int t, int j) const { return A[((size_t)b * m + t) * n + j]; }
+    __device__ float2 loadB(int b, int j, int c) const {
+        const int p = perm[(size_t)b * n + c];
+        const float f = inv[(size_t)b * n + c];
+        const float2 v = W[((size_t)b * n + p) * n + j];
+        return make_float2(v.x * f, v.y * f);
+    }
+    __device__ void store(int b, int t, int c, float2 v) const { U[((size_t)b * m + t) * kmax + c] = v; }
+    __device__ void reduce_add(int b, int c, float v) const { atomicAdd(&norm2[(size_t)b * kmax + c], v); }
+};
+
+// S[b][c] = sqrt(norm2) ; Vt[b][c][:] /= S           (refined singular value = || A^H u_c ||)
+__global__ void __launch_bounds__(256) scale_rows_kernel(float2* __restrict__ Vt, int n, int kmax,
+                                                         const float* __restrict__ norm2,
+                                                         const int32_t* __restrict__ ranks, float* __restrict__ S) {
+    const int b = blockIdx.y, c = blockIdx.x;
+    if (c >= ranks[b]) return;
+    const float s = sqrtf(norm2[(size_t)b * kmax + c]);
+    if (threadIdx.x == 0) S[(size_t)b * kmax + c] = s;
+    const float f = s > 0.f ? 1.f / s : 0.f;
+    float2* d = Vt + ((size_t)b * kmax + c) * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) {
+        float2 v = d[x];
+        v.x *= f;
+        v.y *= f;
+        d[x] = v;
+    }
+}
+__global__ void __launch_bounds__(256) scale_cols_kernel(float2* __restrict__ U, int m, int kmax,
+                                                         const float* __restrict__ norm2,
+                                                         const int32_t* __restrict__ ranks, float* __restrict__ S) {
+    const int b = blockIdx.y;
+    const int k = ranks[b];
+    const size_t tot = (size_t)m * kmax;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % kmax);
+        if (c < k) {
+            const float s = sqrtf(norm2[(size_t)b * kmax + c]);
+            const float f = s > 0.f ? 1.f / s : 0.f;
+            float2 v = U[(size_t)b * tot + e];
+            v.x *= f;
+            v.y *= f;
+            U[(size_t)b * tot + e] = v;
+            if (e < (size_t)kmax) S[(size_t)b * kmax + c] = s;
+        }
+    }
+}
+__global__ void retained_energy_kernel(const float* __restrict__ S, int kmax, int B, float* __restrict__ stats) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        double e = 0.0;
+        for (int c = 0; c < kmax; ++c) e += (double)S[(size_t)b * kmax + c] * (double)S[(size_t)b * kmax + c];
+        stats[4 * b + 1] = (float)e;
+    }
+}
+
+// =================================================================================================================
+// Reconstruction                                         reference: reconstruct_vis, decompress_ms.py:107-131
+// =================================================================================================================
+struct ReconOp {  // out[t][v] = sum_c (U[t][c] S[c]) Vt[c][v]
+    const float2* U;
+    const float* S;
+    const float2* Vt;
+    const int32_t* ranks;
+    float2* out;
+    int m, n, kmax;
+    static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
+    static constexpr int REDUCE = 0;
+    __device__ int M(int) const { return m; }
+    __device__ int N(int) const { return n; }
+    __device__ int K(int b) const {
+        if (!ranks) return kmax;
+        const int k = ranks[b];
+        return k < kmax ? (k < 0 ? 0 : k) : kmax;
+    }
+    __host__ __device__ int Mfill() const { return m; }
+    __host__ __device__ int Nfill() const { return n; }
+    __device__ float2 loadA(int b, int t, int c) const {
+        const float2 u = U[((size_t)b * m + t) * kmax + c];
+        const float s = S[(size_t)b * kmax + c];
+        return make_float2(u.x * s, u.y * s);
+    }
+    __device__ float2 loadB(int b, int c, int j) const { return Vt[((size_t)b * kmax + c) * n + j]; }
+    __device__ void store(int b, int t, int j, float2 v) const { out[((size_t)b * m + t) * n + j] = v; }
+    __device__ void reduce_add(int, int, float) const {}
+};
+
+// =================================================================================================================
+// Synthetic MeerKAT-like visibilities
+// =================================================================================================================
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+
+__global__ void __launch_bounds__(256)
+synth_kernel(float2* __restrict__ A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,
+             uint64_t seed) {
+    constexpr int NSRC = 10;
+    __shared__ float rho[NSRC], phi[NSRC];
+    const int bc = blockIdx.y;  // local matrix index = bl * ncorr + corr
+    const int bl = bc / ncorr, corr = bc - bl * ncorr;
+    const int gbl = bl_offset + bl;
+    if (threadIdx.x < NSRC) {
+        const uint64_t k = mix64(seed ^ mix64(0x51ull + (uint64_t)gbl * 64 + threadIdx.x));
+        const float R = 30.f * (float)(gbl + 1) / (float)nbl_total;
+        rho[threadIdx.x] = (2.f * u01(k) - 1.f) * R;
+        phi[threadIdx.x] = 6.2831853f * u01(mix64(k));
+    }
+    __syncthreads();
+    const float gain = (corr == 0 || corr == ncorr - 1) ? 1.f : 0.01f;
+    const size_t per = (size_t)m * n;
+    float2* Ab = A + (size_t)bc * per;
+    const uint64_t key = mix64(seed ^ mix64(0xABCDull + (uint64_t)gbl * 16 + corr));
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e / n), v = (int)(e - (size_t)t * n);
+        const float ft = (float)t / (float)m;
+        const float fv = 1.f + 0.2f * (float)v / (float)n;
+        float re = 0.f, im = 0.f;
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) {
+            float sn, cs;
+            sincosf(6.2831853f * rho[s] * ft * fv + phi[s], &sn, &cs);
+            re += cs;
+            im += sn;
+        }
+        const uint64_t hh = mix64(key ^ (uint64_t)e);
+        const float u1 = u01(hh), u2 = u01(mix64(hh));
+        const float rad = sqrtf(-2.f * logf(u1)) * 0.70710678f;
+        float sn, cs;
+        sincosf(6.2831853f * u2, &sn, &cs);
+        Ab[e] = make_float2(gain * re + rad * cs, gain * im + rad * sn);
+    }
+}
+
+}  // namespace
+
+// =================================================================================================================
+// launchers
+// =================================================================================================================
+int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int side, float2* W) {
+    if (side == 0) {
+        GramOp0 op{A, W, m, n};
+        return cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
+    }
+    GramOp1 op{A, W, m, n};
+    return cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
+}
+
+int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev) {
+    gram_normalise_kernel<<<B, 256, 0, h->stream>>>(W, r, gscale_dev, nonfinite_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_launch_pack_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, int ld, float* gscale_dev,
+                         int32_t* nonfinite_dev) {
+    pack_small_kernel<<<B, 256, 0, h->stream>>>(A, m, n, W, ld, gscale_dev, nonfinite_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int ld, const float* gscale_dev,
+                     int mode_gram, int fixed_rank, float decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
+                     float* S_dev, int32_t* ranks_dev, float* stats_dev, const int32_t* sweeps_dev,
+                     const int32_t* done_dev) {
+    int P = 1;
+    while (P < r) P <<= 1;
+    const size_t smem = (size_t)P * 12;
+    select_kernel<<<B, 256, smem, h->stream>>>(W, r, ldot, ld, gscale_dev, mode_gram, fixed_rank, decorrelation, kmax,
+                                               perm_dev, inv_dev, S_dev, ranks_dev, stats_dev, sweeps_dev, done_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info) {
+    pack_info_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(sweeps, done, B, info);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_launch_find_n(vk_context* h, const float* S, int B, int r, float decorrelation, int32_t* ranks) {
+    find_n_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(S, B, r, decorrelation, ranks);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+static int launch_rows(vk_context* h, const float2* W, int r, int ld, int off, int len, int kmax, const int32_t* perm,
+                       const float* inv, const int32_t* ranks, int conj, int scaled, float2* dst, int B) {
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        rows_from_vectors_kernel<<<dim3(kmax, nb), 256, 0, h->stream>>>(
+            W + (size_t)b0 * r * ld, r, ld, off, len, kmax, perm + (size_t)b0 * r, inv + (size_t)b0 * r, ranks + b0,
+            conj, scaled, dst + (size_t)b0 * kmax * len);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}
+static int launch_cols(vk_context* h, const float2* W, int r, int ld, int off, int len, int kmax, const int32_t* perm,
+                       const float* inv, const int32_t* ranks, int conj, int scaled, float2* dst, int B) {
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        cols_from_vectors_kernel<<<dim3((len + 31) / 32, (kmax + 31) / 32, nb), 256, 0, h->stream>>>(
+            W + (size_t)b0 * r * ld, r, ld, off, len, kmax, perm + (size_t)b0 * r, inv + (size_t)b0 * r, ranks + b0,
+            conj, scaled, dst + (size_t)b0 * len * kmax);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}
+
+int vk_launch_factors_small(vk_context* h, const float2* W, int ld, int B, int m, int n, int kmax,
+                            const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float2* U,
+                            float2* Vt) {
+    const int r = m <= n ? m : n;
+    int rc;
+    if (m <= n) {
+        // vectors = rotated rows of A (length n) then accumulated rotations R (length m): Vt = row / sigma, U = R^H
+        if ((rc = launch_rows(h, W, r, ld, 0, n, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, Vt, B))) return rc;
+        if ((rc = launch_cols(h, W, r, ld, n, m, kmax, perm_dev, inv_dev, ranks_dev, 1, 0, U, B))) return rc;
+    } else {
+        // vectors = rotated columns of A (length m) then accumulated rotations (length n): U = col / sigma, Vt = M^H
+        if ((rc = launch_cols(h, W, r, ld, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
+        if ((rc = launch_rows(h, W, r, ld, m, n, kmax, perm_dev, inv_dev, ranks_dev, 1, 0, Vt, B))) return rc;
+    }
+    return VK_OK;
+}
+
+int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int B, int m, int n, int side, int kmax,
+                           const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float* norm2_dev,
+                           float2* U, float* S, float2* Vt, float* stats_dev) {
+    int rc;
+    VK_CUDA(h, cudaMemsetAsync(norm2_dev, 0, sizeof(float) * (size_t)B * kmax, h->stream));
+    if (side == 0) {
+        const int r = m;
+        if ((rc = launch_cols(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
+        FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
+        if (kmax <= 8)
+            rc = cgemm_launch<8, 256, 8, 2, 16>(h, op, B);
+        else if (kmax <= 32)
+            rc = cgemm_launch<32, 128, 4, 4, 16>(h, op, B);
+        else
+            rc = cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
+        if (rc) return rc;
+        for (int b0 = 0; b0 < B; b0 += 65535) {
+            const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+            scale_rows_kernel<<<dim3(kmax, nb), 256, 0, h->stream>>>(Vt + (size_t)b0 * kmax * n, n, kmax,
+                                                                      norm2_dev + (size_t)b0 * kmax, ranks_dev + b0,
+                                                                      S + (size_t)b0 * kmax);
+            VK_LAUNCH_CHECK(h);
+        }
+    } else {
+        const int r = n;
+        if ((rc = launch_rows(h, W, r, r, 0, n, kmax, perm_dev, inv_dev, ranks_dev, 1, 1, Vt, B))) return rc;
+        FormUOp op{A, W, perm_dev, inv_dev, ranks_dev, U, norm2_dev, m, n, kmax};
+        if (kmax <= 8)
+            rc = cgemm_launch<256, 8, 2, 8, 16>(h, op, B);
+        else if (kmax <= 32)
+            rc = cgemm_launch<128, 32, 4, 4, 16>(h, op, B);
+        else
+            rc = cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
+        if (rc) return rc;
+        for (int b0 = 0; b0 < B; b0 += 65535) {
+            const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+            int gx = (int)(((size_t)m * kmax + 255) / 256);
+            if (gx > 64) gx = 64;
+            scale_cols_kernel<<<dim3(gx, nb), 256, 0, h->stream>>>(U + (size_t)b0 * m * kmax, m, kmax,
+                                                                    norm2_dev + (size_t)b0 * kmax, ranks_dev + b0,
+                                                                    S + (size_t)b0 * kmax);
+            VK_LAUNCH_CHECK(h);
+        }
+    }
+    retained_energy_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(S, kmax, B, stats_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
+                          int m, int n, int kmax, float2* out) {
+    ReconOp op{U, S, Vt, ranks, out, m, n, kmax};
+    return cgemm_launch<64, 64, 4, 4, 8>(h, op, B);
+}
+
+int vk_launch_synth(vk_context* h, float2* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,
+                    uint64_t seed) {
+    const int nmat = nbl_local * ncorr;
+    int gx = (int)(((size_t)m * n + 255) / 256);
+    if (gx > 128) gx = 128;
+    for (int b0 = 0; b0 < nmat; b0 += 65532) {  // multiple of 4 keeps (bl, corr) decoding intact for ncorr | 65532
+        int nb = nmat - b0;
+        if (nb > 65532) nb = 65532;
+        if (b0 % ncorr != 0) return vk_fail(h, VK_EINVAL, "synth: ncorr must divide 65532");
+        synth_kernel<<<dim3(gx, nb), 256, 0, h->stream>>>(A + (size_t)b0 * m * n, nbl_local, ncorr, m, n,
+                                                          bl_offset + b0 / ncorr, nbl_total, seed);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}
