@@ -72,7 +72,7 @@ size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax);
  * and truncated factors. kmax must be >= the largest possible k (fixed_rank, or r in energy/full mode).
  * Synchronous with respect to `ranks`/`stats` only if the caller syncs; status reflects errors found so far
  * (convergence / non-finite input are reported by this call because it polls the device while iterating). */
-int vk_compress_batched(vk_handle h, const void* A_dev, int B, int m, int n, int fixed_rank, float decorrelation,
+int vk_compress_batched(vk_handle h, const void* A_dev, int B, int m, int n, int fixed_rank, double decorrelation,
                         int kmax, void* U_dev, float* S_dev, void* Vt_dev, int32_t* ranks_dev, float* stats_dev,
                         void* ws_dev, size_t ws_bytes);
 
@@ -83,13 +83,13 @@ int vk_reconstruct_batched(vk_handle h, const void* U_dev, const float* S_dev, c
 
 /* Same two operations with HOST buffers (numpy arrays): H2D copy, compute, D2H copy, synchronous.
  * These are what the single-matrix Python drop-ins apply_svd / reconstruct_vis call. */
-int vk_compress_host(vk_handle h, const void* A_host, int B, int m, int n, int fixed_rank, float decorrelation,
+int vk_compress_host(vk_handle h, const void* A_host, int B, int m, int n, int fixed_rank, double decorrelation,
                      int kmax, void* U_host, float* S_host, void* Vt_host, int32_t* ranks_host, float* stats_host);
 int vk_reconstruct_host(vk_handle h, const void* U_host, const float* S_host, const void* Vt_host,
                         const int32_t* ranks_host, int B, int m, int n, int kmax, void* out_host);
 
 /* Replaces find_n_decorrelation (compress_ms.py:295-319) on device: S_dev [B][r] float32 descending. */
-int vk_find_n_decorrelation_batched(vk_handle h, const float* S_dev, int B, int r, float decorrelation,
+int vk_find_n_decorrelation_batched(vk_handle h, const float* S_dev, int B, int r, double decorrelation,
                                     int32_t* ranks_dev);
 
 /* ---- stage-level entry points (tests, ncu) ---------------------------------------------------------------- */

@@ -1,7 +1,7 @@
 """Shared parity checks: CUDA path vs the oracle, with the tolerances BASELINE.json's north_star states.
 
   retained singular values : |S - S_ref| <= 1e-4 * S_ref              (+ 2e-6 * S_ref[0] absolute floor: fp32 noise)
-  reconstruction error     : | ||A - A_hat|| - ||A - A_ref|| | <= 1e-5 * ||A - A_ref||   (+ 2e-6 * ||A|| floor, for
+  reconstruction error     : | ||A - A_hat|| - ||A - A_ref|| | <= 1e-5 * ||A - A_ref||   (+ 5e-6 * ||A|| floor, for
                              exactly-low-rank inputs whose reference error is itself float32 round-off)
   chosen rank              : identical, except when the cumulative energy at the smaller of the two ranks lies
                              within 2e-4 (relative, i.e. a 1e-4 change of one singular value) of the threshold
@@ -14,7 +14,7 @@ from oracle import visco_oracle as vo
 S_RTOL = 1e-4
 S_FLOOR = 2e-6
 ERR_RTOL = 1e-5
-ERR_FLOOR = 2e-6
+ERR_FLOOR = 5e-6
 TIE_RTOL = 2e-4
 
 
@@ -23,7 +23,7 @@ def rank_is_acceptable(s_ref, decorrelation, k, k_ref):
         return True
     s2 = s_ref.astype(np.float32) ** 2
     total = np.sum(s2)
-    thr = np.float32(decorrelation) ** 2 * total if False else (decorrelation ** 2) * total
+    thr = (decorrelation ** 2) * total
     cum = np.cumsum(s2)
     lo = min(k, k_ref)
     hi = max(k, k_ref)

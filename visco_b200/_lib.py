@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libvisco_b200.so")
 
 VK_OK, VK_EINVAL, VK_ENOMEM, VK_ECUDA, VK_ENOCONV, VK_ENONFINITE = range(6)
 
-_vp, _i, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64
+_vp, _i, _f, _d, _sz, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_uint64
 
 # name -> (restype, argtypes): exactly the declarations of include/visco_b200.h
 SIGNATURES = {
@@ -20,11 +20,11 @@ SIGNATURES = {
     "vk_sync": (_i, [_vp]),
     "vk_set_option": (_i, [_vp, C.c_char_p, C.c_double]),
     "vk_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
-    "vk_compress_batched": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "vk_compress_batched": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
     "vk_reconstruct_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "vk_compress_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vk_compress_host": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "vk_reconstruct_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "vk_find_n_decorrelation_batched": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "vk_find_n_decorrelation_batched": (_i, [_vp, _vp, _i, _i, _d, _vp]),
     "vk_gram_batched": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vk_eigh_jacobi_batched": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "vk_svd_jacobi_small_batched": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -84,7 +84,7 @@ struct StageTimer {
     }
 };
 
-int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
                    float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L) {
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
@@ -242,6 +242,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_bsz = (int)v;
     else if (k == "stage_timing")
         h->stage_timing = (int)v;
+    else if (k == "jacobi_generic")
+        h->jacobi_generic = (int)v;
     else if (k == "chunk")
         h->chunk = (int)v;
     else
@@ -259,7 +261,7 @@ size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax) {
 int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(m, n)) ? 1 : 0; }
 int vk_gram_uses_tcgen05(int m, int n, int side) { return vk_gram_tc_supported(m, n, side) ? 1 : 0; }
 
-int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
                         void* U, float* S, void* Vt, int32_t* ranks, float* stats, void* ws, size_t ws_bytes) {
     int rc = check_common(h, B, m, n, kmax);
     if (rc) return rc;
@@ -269,7 +271,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     const int need_k = fixed_rank > 0 ? (fixed_rank < r ? fixed_rank : r) : r;
     if (kmax < need_k) return vk_fail(h, VK_EINVAL, "kmax smaller than the largest possible rank");
     if (kmax > r) return vk_fail(h, VK_EINVAL, "kmax larger than min(m, n)");
-    if (decorrelation < 0.f || !(decorrelation == decorrelation))
+    if (decorrelation < 0.0 || !(decorrelation == decorrelation))
         return vk_fail(h, VK_EINVAL, "decorrelation must be >= 0");
     VK_CUDA(h, cudaSetDevice(h->device));
     int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n);
@@ -314,7 +316,7 @@ int vk_reconstruct_batched(vk_handle h, const void* U, const float* S, const voi
                                  kmax, static_cast<float2*>(out));
 }
 
-int vk_find_n_decorrelation_batched(vk_handle h, const float* S, int B, int r, float decorrelation, int32_t* ranks) {
+int vk_find_n_decorrelation_batched(vk_handle h, const float* S, int B, int r, double decorrelation, int32_t* ranks) {
     if (!h) return VK_EINVAL;
     if (B < 0 || r < 1 || !S || !ranks) return vk_fail(h, VK_EINVAL, "bad argument");
     if (B == 0) return VK_OK;
@@ -322,7 +324,7 @@ int vk_find_n_decorrelation_batched(vk_handle h, const float* S, int B, int r, f
     return vk_launch_find_n(h, S, B, r, decorrelation, ranks);
 }
 
-int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, float decorrelation, int kmax,
+int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
                      void* U, float* S, void* Vt, int32_t* ranks, float* stats) {
     int rc = check_common(h, B, m, n, kmax);
     if (rc) return rc;

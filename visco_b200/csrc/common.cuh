@@ -29,6 +29,7 @@ struct vk_context {
     int jacobi_bsz = 0;  // 0 = auto
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
+    int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -106,11 +107,11 @@ int vk_launch_pack_small(vk_context* h, const float2* A, int B, int m, int n, fl
 
 // norms of the vectors, sort, sigma, rank choice. mode_gram: sigma = sqrt(norm * gscale) else sigma = norm * gscale
 int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int ld, const float* gscale_dev,
-                     int mode_gram, int fixed_rank, float decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
+                     int mode_gram, int fixed_rank, double decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
                      float* S_dev, int32_t* ranks_dev, float* stats_dev, const int32_t* sweeps_dev,
                      const int32_t* done_dev);
 int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info);
-int vk_launch_find_n(vk_context* h, const float* S, int B, int r, float decorrelation, int32_t* ranks);
+int vk_launch_find_n(vk_context* h, const float* S, int B, int r, double decorrelation, int32_t* ranks);
 
 // factor formation
 int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int B, int m, int n, int side, int kmax,

@@ -143,15 +143,40 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restric
 // Selection: norms -> sort -> sigma -> rank              reference: compress_ms.py:295-319 (energy rule, float32),
 //                                                                   compress_ms.py:352-361 (precedence, slicing)
 // =================================================================================================================
-__device__ __forceinline__ int energy_rank(const float* sig, int r, float decorrelation) {
-    // total = sum(S^2) ; threshold = float32(dec^2) * total ; cumulative = cumsum(S^2) ; argmax(cum >= thr) + 1
-    double tot = 0.0;
-    for (int c = 0; c < r; ++c) tot += (double)(sig[c] * sig[c]);
-    const float total = (float)tot;
-    const float thr = (float)((double)decorrelation * (double)decorrelation) * total;
+// numpy's float32 add-reduce (np.sum of a contiguous array): pairwise summation with an 8-way unrolled leaf of at most
+// 128 elements (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum). Restated so that the energy rule sees
+// the same float32 total the reference sees — at decorrelation = 1.0 the reference's answer hinges on whether the
+// sequential cumsum reaches this pairwise total (it returns rank 1 when it does not).
+__device__ float np_pairwise_sum_sq(const float* a, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, __fmul_rn(a[i], a[i]));
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = __fmul_rn(a[j], a[j]);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], __fmul_rn(a[i + j], a[i + j]));
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, __fmul_rn(a[i], a[i]));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum_sq(a, n2), np_pairwise_sum_sq(a + n2, n - n2));
+}
+
+__device__ int energy_rank(const float* sig, int r, double decorrelation) {
+    // total = np.sum(S**2) ; threshold = float32(dec**2) * total ; cumulative = np.cumsum(S**2) ;
+    // n = argmax(cumulative >= threshold) + 1          (reference compress_ms.py:311-315, all float32)
+    const float total = np_pairwise_sum_sq(sig, r);
+    const float thr = __fmul_rn((float)(decorrelation * decorrelation), total);
     float cum = 0.f;
     for (int c = 0; c < r; ++c) {
-        cum += sig[c] * sig[c];
+        cum = __fadd_rn(cum, __fmul_rn(sig[c], sig[c]));  // no FMA contraction: numpy squares, then adds
         if (cum >= thr) return c + 1;
     }
     return 1;  // argmax of an all-False array is 0
@@ -159,7 +184,7 @@ __device__ __forceinline__ int energy_rank(const float* sig, int r, float decorr
 
 __global__ void __launch_bounds__(256)
 select_kernel(const float2* __restrict__ W, int r, int ldot, int ld, const float* __restrict__ gscale, int mode_gram,
-              int fixed_rank, float decorrelation, int kmax, int32_t* __restrict__ perm, float* __restrict__ inv,
+              int fixed_rank, double decorrelation, int kmax, int32_t* __restrict__ perm, float* __restrict__ inv,
               float* __restrict__ S, int32_t* __restrict__ ranks, float* __restrict__ stats,
               const int32_t* __restrict__ sweeps, const int32_t* __restrict__ done) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -222,7 +247,7 @@ select_kernel(const float2* __restrict__ W, int r, int ldot, int ld, const float
         int k;
         if (fixed_rank > 0)
             k = fixed_rank < r ? fixed_rank : r;
-        else if (decorrelation > 0.f)
+        else if (decorrelation > 0.0)
             k = energy_rank(sig, r, decorrelation);
         else
             k = r;
@@ -259,7 +284,7 @@ __global__ void pack_info_kernel(const int32_t* __restrict__ sweeps, const int32
     }
 }
 
-__global__ void find_n_kernel(const float* __restrict__ S, int B, int r, float decorrelation,
+__global__ void find_n_kernel(const float* __restrict__ S, int B, int r, double decorrelation,
                               int32_t* __restrict__ ranks) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) ranks[b] = energy_rank(S + (size_t)b * r, r, decorrelation);
@@ -524,7 +549,7 @@ int vk_launch_pack_small(vk_context* h, const float2* A, int B, int m, int n, fl
 }
 
 int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int ld, const float* gscale_dev,
-                     int mode_gram, int fixed_rank, float decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
+                     int mode_gram, int fixed_rank, double decorrelation, int kmax, int32_t* perm_dev, float* inv_dev,
                      float* S_dev, int32_t* ranks_dev, float* stats_dev, const int32_t* sweeps_dev,
                      const int32_t* done_dev) {
     int P = 1;
@@ -542,7 +567,7 @@ int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* don
     return VK_OK;
 }
 
-int vk_launch_find_n(vk_context* h, const float* S, int B, int r, float decorrelation, int32_t* ranks) {
+int vk_launch_find_n(vk_context* h, const float* S, int B, int r, double decorrelation, int32_t* ranks) {
     find_n_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(S, B, r, decorrelation, ranks);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
