@@ -141,6 +141,21 @@ def test_gram_stage_simt(eng, torch):
             np.testing.assert_allclose(W[b], G.T, atol=2e-6 * np.abs(G).max())
 
 
+def test_gram_stage_tcgen05(eng, torch):
+    """tcgen05 + TMA Gram kernel (3xTF32, two-level accumulation) against an fp64 Gram; includes ragged tiles
+    (m not a multiple of 128) and a K tail (2n not a multiple of 32)."""
+    for (B, m, n) in [(2, 128, 256), (3, 256, 1024), (2, 200, 300), (2, 512, 1024), (2, 130, 130), (1, 96, 2050)]:
+        assert eng.gram_uses_tcgen05(m, n)
+        A = _device_cube(eng, torch, B, 1, m, n, nbl_total=8)
+        W = eng.gram(A, impl=2).cpu().numpy()
+        a = A.cpu().numpy().astype(np.complex128)
+        G = np.einsum("btv,biv->bit", a, a.conj())
+        assert np.abs(W - G).max() <= 3e-6 * np.abs(G).max(), (m, n, np.abs(W - G).max() / np.abs(G).max())
+        # Hermitian: off-diagonal tiles are mirrored exactly, diagonal tiles agree to accumulation-order rounding
+        np.testing.assert_allclose(W, W.conj().transpose(0, 2, 1), atol=1e-6 * np.abs(G).max())
+    assert not eng.gram_uses_tcgen05(64, 4096) and not eng.gram_uses_tcgen05(300, 200)
+
+
 def test_eigh_stage(eng, torch):
     m, n = 160, 400
     A = _device_cube(eng, torch, 2, 2, m, n)

@@ -1,6 +1,363 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Batched complex Gram product W = (A A^H)^T on the 5th-generation tensor cores (north_star item (a)).
+//
+//   W[b][i][t] = sum_v A[b][t][v] * conj(A[b][i][v])          i, t < m ; v < n ; complex64, row-major
+//
+// replaces the O(m^2 n) part of the LAPACK cgesdd call under da.linalg.svd (reference visco/compress_ms.py:350).
+//
+// Formulation. View A[b] as a REAL m x 2n matrix R (re, im interleaved — exactly how complex64 sits in memory):
+//   Re W[i][t] = R_i . R_t                       Im W[i][t] = R_i . Q_t ,   Q_t[2v] = R_t[2v+1], Q_t[2v+1] = -R_t[2v]
+// so one real MMA with the stacked B operand [R_J ; Q_J] (N = 256) yields the real part in TMEM columns 0..127 and
+// the imaginary part in columns 128..255 of a 128 x 128 complex output tile. No tensor-core format carries 24
+// mantissa bits, so each fp32 operand is split hi + lo (both TF32, round-to-nearest) and the product is formed as
+// hi*hi + hi*lo + lo*hi ("3xTF32"). The tensor core adds into its fp32 accumulator with truncation (measured: a
+// relative bias of ~3e-8 per MMA, 2.5e-5 after the 768 MMAs of n = 1024), so accumulation is two-level: MMAs chain for
+// only CHUNK_KB K-blocks (48 MMAs) into one of two ping-pong TMEM accumulators, and the finished chunk is promoted
+// into fp32 registers with round-to-nearest adds while the tensor core fills the other buffer.
+//
+// Kernel: one CTA per upper-triangular 128 x 128 tile pair (I <= J) of one matrix; the mirrored tile is written as the
+// conjugate transpose. Warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes of 128 rows x 32
+// floats), warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4..11 = converters (split raw fp32 tiles into
+// hi/lo and the swapped copy, in place, swizzle-agnostic because the split is element-wise within 16-byte chunks)
+// and promoters (tcgen05.ld of finished chunks -> register accumulators -> global at the end). The converter warps
+// raise their register budget with setmaxnreg (128 accumulators per thread); the other warps give theirs up.
+#include <cuda.h>
+
 #include "common.cuh"
-bool vk_gram_tc_supported(int, int, int) { return false; }
-int vk_launch_gram_tc(vk_context* h, const float2*, int, int, int, float2*) {
-    return vk_fail(h, VK_EINVAL, "tcgen05 Gram not built");
+
+namespace {
+
+constexpr int TILE = 128;             // rows of a tile (both I and J)
+constexpr int KB_FLOATS = 32;         // K-block: 32 floats = 128 bytes = one SWIZZLE_128B row
+constexpr int NSTAGE = 2;
+constexpr uint32_t A_TILE_BYTES = TILE * 128;          // 16 KiB
+constexpr uint32_t B_TILE_BYTES = 2 * TILE * 128;      // 32 KiB (R_J rows then Q_J rows)
+constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES, OFF_B_HI = 2 * A_TILE_BYTES,
+                   OFF_B_LO = 2 * A_TILE_BYTES + B_TILE_BYTES;
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KiB
+constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + 128 + 1024;  // + barriers + alignment slack
+constexpr int NUM_CONVERTERS = 256;
+constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
+constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulators (re | im), ping-pong
+constexpr int CHUNK_KB = 4;           // K-blocks per TMEM accumulation chain (4 x 12 = 48 MMAs)
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor fields)
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major) bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+// hi/lo split of one 16-byte chunk
+struct Split4 {
+    float4 hi, lo;
+};
+__device__ __forceinline__ Split4 split4(float4 v) {
+    Split4 s;
+    s.hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    s.lo = make_float4(to_tf32(v.x - s.hi.x), to_tf32(v.y - s.hi.y), to_tf32(v.z - s.hi.z), to_tf32(v.w - s.hi.w));
+    return s;
+}
+// (r0, i0, r1, i1) -> (i0, -r0, i1, -r1)
+__device__ __forceinline__ float4 swap_neg(float4 v) { return make_float4(v.y, -v.x, v.w, -v.z); }
+
+// Promote one finished accumulation chunk: TMEM (this warp's 32 lanes x 64 re + 64 im columns) -> += registers.
+__device__ __forceinline__ void drain_chunk(int c, uint32_t bar_accf, uint32_t bar_acce, uint32_t tmem_base, int quad,
+                                            int chalf, float (&acc_re)[64], float (&acc_im)[64]) {
+    const int p = c & 1;
+    mbar_wait(bar_accf + 8 * p, ((uint32_t)c >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * 256 + chalf * 64);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t re[16], im[16];
+        tmem_ld16(taddr + g * 16, re);
+        tmem_ld16(taddr + 128 + g * 16, im);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc_re[g * 16 + j] += __uint_as_float(re[j]);
+            acc_im[g * 16 + j] += __uint_as_float(im[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(bar_acce + 8 * p);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W, int m, int n2, int tiles_per_mat,
+               int T) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + OFF_BARS;
+    // barrier slots (8 bytes each): raw_full[s] @0,8 ; conv_full[s] @16,24 ; empty[s] @32,40 ; acc_full[p] @48,56 ;
+    // acc_empty[p] @64,72 ; tmem ptr @96
+    const uint32_t bar_raw = bars, bar_conv = bars + 16, bar_empty = bars + 32, bar_accf = bars + 48,
+                   bar_acce = bars + 64;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 96);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / tiles_per_mat;
+    int tile = blockIdx.x - b * tiles_per_mat;
+    // decode upper-triangular tile index -> (I, J), I <= J
+    int I = 0;
+    while (tile >= T - I) {
+        tile -= T - I;
+        ++I;
+    }
+    const int J = I + tile;
+    const int KB = (n2 + KB_FLOATS - 1) / KB_FLOATS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_raw + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, NUM_CONVERTERS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int p = 0; p < 2; ++p) {
+            mbar_init(bar_accf + 8 * p, 1);
+            mbar_init(bar_acce + 8 * p, NUM_CONVERTERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int NC = (KB + CHUNK_KB - 1) / CHUNK_KB;  // accumulation chunks
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+      if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
+                mbar_wait(bar_empty + 8 * s, (use & 1) ^ 1);
+                const uint32_t st = sbase + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_raw + 8 * s, 2 * A_TILE_BYTES);
+                tma_load_3d(st + OFF_A_HI, &tmap, bar_raw + 8 * s, kb * KB_FLOATS, I * TILE, b);
+                tma_load_3d(st + OFF_B_HI, &tmap, bar_raw + 8 * s, kb * KB_FLOATS, J * TILE, b);
+            }
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = tf32, K-major both, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
+                const int c = kb / CHUNK_KB, p = c & 1;
+                const bool first = (kb % CHUNK_KB) == 0;
+                if (first) {  // the promoters must have drained this accumulator (chunk c - 2)
+                    mbar_wait(bar_acce + 8 * p, (((uint32_t)c >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(bar_conv + 8 * s, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = sbase + s * STAGE_BYTES;
+                const uint64_t a_hi = make_sw128_desc(st + OFF_A_HI), a_lo = make_sw128_desc(st + OFF_A_LO);
+                const uint64_t b_hi = make_sw128_desc(st + OFF_B_HI), b_lo = make_sw128_desc(st + OFF_B_LO);
+                const uint32_t d = tmem_base + (uint32_t)p * 256u;
+#pragma unroll
+                for (int k = 0; k < KB_FLOATS / 8; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 bytes per MMA along K
+                    umma_tf32(d, a_lo + adv, b_hi + adv, idesc, !(first && k == 0));
+                    umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(d, a_hi + adv, b_hi + adv, idesc, 1);
+                }
+                umma_commit(bar_empty + 8 * s);  // frees the stage when these MMAs have read it
+                if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == KB - 1) umma_commit(bar_accf + 8 * p);  // chunk complete
+            }
+        }
+      }
+    } else {
+        // ===================== converters =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int ct = threadIdx.x - 128;
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int chalf = (warp - 4) >> 2;    // which 64-column half of the tile this warp owns
+        float acc_re[64], acc_im[64];         // this thread's row x 64 complex columns, fp32 RN accumulation
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc_re[j] = acc_im[j] = 0.f;
+        int next_drain = 0;
+
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % NSTAGE;
+            const uint32_t use = kb / NSTAGE;
+            mbar_wait(bar_raw + 8 * s, use & 1);
+            unsigned char* st = smem + s * STAGE_BYTES;
+            float4* a_hi = reinterpret_cast<float4*>(st + OFF_A_HI);
+            float4* a_lo = reinterpret_cast<float4*>(st + OFF_A_LO);
+            float4* b_hi = reinterpret_cast<float4*>(st + OFF_B_HI);
+            float4* b_lo = reinterpret_cast<float4*>(st + OFF_B_LO);
+            constexpr int CH = A_TILE_BYTES / 16;  // 1024 chunks per 128-row tile
+#pragma unroll 2
+            for (int i = 0; i < CH / NUM_CONVERTERS; ++i) {
+                const int c = ct + i * NUM_CONVERTERS;
+                const Split4 sa = split4(a_hi[c]);
+                a_hi[c] = sa.hi;
+                a_lo[c] = sa.lo;
+                const Split4 sb = split4(b_hi[c]);
+                b_hi[c] = sb.hi;
+                b_lo[c] = sb.lo;
+                b_hi[c + CH] = swap_neg(sb.hi);
+                b_lo[c + CH] = swap_neg(sb.lo);
+            }
+            // make the generic-proxy writes visible to the tensor core (async proxy), then signal
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_conv + 8 * s);
+            // promote a finished chunk two K-blocks after its last block was converted: its MMAs have retired by
+            // then (the pipeline is NSTAGE = 2 deep), so this wait does not stall the conversion stream
+            if (kb >= CHUNK_KB + 1 && ((kb - 1) % CHUNK_KB) == 0) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc_re, acc_im);
+        }
+        while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc_re, acc_im);
+
+        // ===================== epilogue: registers -> global =====================
+        const int i_loc = quad * 32 + lane;   // row of the tile = TMEM lane
+        const int gi = I * TILE + i_loc;
+        float2* Wb = W + (size_t)b * m * m;
+        if (gi < m) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int gt = J * TILE + chalf * 64 + j;
+                if (gt < m) Wb[(size_t)gi * m + gt] = make_float2(acc_re[j], acc_im[j]);
+            }
+            if (I != J) {
+                // mirrored tile: W[t][i] = conj(W[i][t]); lanes run along i -> coalesced
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int gt = J * TILE + chalf * 64 + j;
+                    if (gt < m) Wb[(size_t)gt * m + gi] = make_float2(acc_re[j], -acc_im[j]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+bool vk_gram_tc_supported(int m, int n, int side) {
+    // wide matrices only (G = A A^H, contraction along the contiguous channel axis); TMA needs 16-byte row strides
+    return side == 0 && m <= n && m > 64 && (n % 2) == 0 && m <= VK_MAX_R;
+}
+
+int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float2* W) {
+    PFN_encodeTiled encode = get_encode();
+    if (!encode) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    const int T = (m + TILE - 1) / TILE;
+    const int tiles = T * (T + 1) / 2;
+    VK_CUDA(h, cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    // the tensor map's outermost dimension is the batch; keep it within what one map may hold and one grid may cover
+    const int maxB = 32768;
+    for (int b0 = 0; b0 < B; b0 += maxB) {
+        const int nb = (B - b0) < maxB ? (B - b0) : maxB;
+        CUtensorMap tmap;
+        const cuuint64_t dims[3] = {(cuuint64_t)2 * n, (cuuint64_t)m, (cuuint64_t)nb};
+        const cuuint64_t strides[2] = {(cuuint64_t)2 * n * sizeof(float), (cuuint64_t)m * 2 * n * sizeof(float)};
+        const cuuint32_t box[3] = {KB_FLOATS, TILE, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                  const_cast<float2*>(A + (size_t)b0 * m * n), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        gram_tc_kernel<<<(unsigned)(nb * tiles), NUM_THREADS, SMEM_BYTES, h->stream>>>(
+            tmap, W + (size_t)b0 * m * m, m, 2 * n, tiles, T);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
 }
