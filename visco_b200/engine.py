@@ -189,16 +189,22 @@ class Engine:
         return U, S, Vt, info
 
     # ------------------------------------------------------------------------------------------ host API
-    def compress_host(self, A: np.ndarray, decorrelation=None, compressionrank=None):
-        """numpy [B, m, n] complex64 in, padded numpy factors + ranks + stats out (vk_compress_host)."""
+    def compress_host(self, A: np.ndarray, decorrelation=None, compressionrank=None, out=None):
+        """numpy [B, m, n] complex64 in, padded numpy factors + ranks + stats out (vk_compress_host).
+        `out` = (U, S, Vt, ranks, stats) lets the caller supply (pinned) result buffers."""
         A = np.ascontiguousarray(A, dtype=np.complex64)
         B, m, n = A.shape
         kmax = self.rank_bound(m, n, compressionrank, decorrelation)
-        U = np.empty((B, m, kmax), np.complex64)
-        S = np.empty((B, kmax), np.float32)
-        Vt = np.empty((B, kmax, n), np.complex64)
-        ranks = np.empty((B,), np.int32)
-        stats = np.empty((B, 4), np.float32)
+        if out is None:
+            U = np.empty((B, m, kmax), np.complex64)
+            S = np.empty((B, kmax), np.float32)
+            Vt = np.empty((B, kmax, n), np.complex64)
+            ranks = np.empty((B,), np.int32)
+            stats = np.empty((B, 4), np.float32)
+        else:
+            U, S, Vt, ranks, stats = out
+            assert U.shape == (B, m, kmax) and S.shape == (B, kmax) and Vt.shape == (B, kmax, n)
+            assert all(x.flags.c_contiguous for x in out)
         with self._lock:
             self.lib.vk_set_stream(self.h, C.c_void_p(0))
             rc = self.lib.vk_compress_host(self.h, A.ctypes.data, B, m, n, int(compressionrank or 0),
@@ -207,7 +213,7 @@ class Engine:
         self._check(rc, "vk_compress_host")
         return U, S, Vt, ranks, stats
 
-    def reconstruct_host(self, U: np.ndarray, S: np.ndarray, Vt: np.ndarray, ranks=None):
+    def reconstruct_host(self, U: np.ndarray, S: np.ndarray, Vt: np.ndarray, ranks=None, out=None):
         U = np.ascontiguousarray(U, dtype=np.complex64)
         S = np.ascontiguousarray(S, dtype=np.float32)
         Vt = np.ascontiguousarray(Vt, dtype=np.complex64)
@@ -215,7 +221,9 @@ class Engine:
         n = Vt.shape[2]
         if S.shape != (B, kmax) or Vt.shape[:2] != (B, kmax):
             raise ValueError(f"inconsistent factor shapes U{U.shape} S{S.shape} Vt{Vt.shape}")
-        out = np.empty((B, m, n), np.complex64)
+        if out is None:
+            out = np.empty((B, m, n), np.complex64)
+        assert out.shape == (B, m, n) and out.dtype == np.complex64 and out.flags.c_contiguous
         rp = None
         if ranks is not None:
             rp = np.ascontiguousarray(ranks, dtype=np.int32)
