@@ -242,6 +242,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_bsz = (int)v;
     else if (k == "stage_timing")
         h->stage_timing = (int)v;
+    else if (k == "recon_generic")
+        h->recon_generic = (int)v;
     else if (k == "jacobi_generic")
         h->jacobi_generic = (int)v;
     else if (k == "chunk")

@@ -29,6 +29,7 @@ struct vk_context {
     int jacobi_bsz = 0;  // 0 = auto
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
+    int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -27,27 +27,49 @@ __device__ __forceinline__ void rr_pair(int n, int q, int p, int& a, int& b) {
     }
 }
 
-// Correctly rounded 1/sqrt(x). The rotation's cosine and the phase normalisation must be UNBIASED: a systematic
-// 1-ulp error in c makes every rotation shrink (or grow) its vectors and, over ~600 rotations per vector, shows up as
-// a 1e-5 relative error in U S Vt (measured); the SFU approximation rsqrtf() has such a bias.
-__device__ __forceinline__ float rsqrt_nr(float x) { return __frsqrt_rn(x); }
-
-// c, w (complex sine) and t for the pair with squared norms a, b and inner product z = x^H y, |z|^2 = zz > 0
+// Rotation for the pair with squared norms a, b and inner product z = x^H y (zz = |z|^2 > 0):
+//   x' = c x - conj(w) y ,  y' = w x + c y ,  w = c t e^{i arg z},  t = sign(d) |z| / (|d| + sqrt(d^2 + |z|^2)),  d = (b-a)/2.
+// Written so that 1/|z| is never needed:  g = 1 / (|d| + h), h = sqrt(d^2 + zz)  gives  t^2 = zz g^2,  w = z * (c g sign d)
+// and the norm transfer t |z| = sign(d) zz g. The rotation is unitary iff c^2 (1 + zz g^2) = 1 for the g actually used,
+// so h and g may come from the fast SFU approximations (they only steer convergence) and only c must be accurate AND
+// unbiased. Late sweeps apply thousands of tiny rotations whose u = 1 + t^2 = 1 + j 2^-23 has the exact answer
+// c = 1 - j 2^-24: any intermediate that is rounded first (1.0f / sqrtf(u), or a Newton residual built from a rounded
+// product) turns odd j into ties, ties-to-even favours the frequent small j, and the resulting ~2e-8 systematic error per
+// rotation showed up as a 1e-5 relative error in U S Vt after ~600 rotations per vector (measured; correctly rounded c
+// gives 1e-6). u lies in [1, 2], so no special cases: rsqrtf + one Newton step whose residual 1 - u y^2 is evaluated
+// exactly with an error-free product (two fmas), then a single final rounding.
+__device__ __forceinline__ float rsqrt_unit(float u) {
+    const float y = rsqrtf(u);
+    const float p = u * y;
+    const float pe = fmaf(u, y, -p);   // u y = p + pe exactly
+    float e = fmaf(-p, y, 1.f);        // 1 - p y   (exact up to ~1e-15)
+    e = fmaf(-pe, y, e);               // 1 - u y^2
+    return fmaf(0.5f * y, e, y);
+}
 __device__ __forceinline__ void rotation_params(float a, float b, float zr, float zi, float zz, float& c, float& wr,
                                                 float& wi, float& taz) {
-    // fast SFU ops where only convergence speed is at stake (tau, t); exact ones where unitarity is (c, 1/|z|)
-    const float rz = rsqrt_nr(zz);  // 1 / |z|
-    const float az = zz * rz;       // |z|
-    const float tau = 0.5f * (b - a) * rz;
-    const float atau = fabsf(tau);
-    const float x = fmaf(tau, tau, 1.f);
-    float t = atau > 1e15f ? __fdividef(0.5f, atau) : __fdividef(1.f, atau + x * rsqrtf(x));
-    t = tau >= 0.f ? t : -t;
-    c = rsqrt_nr(fmaf(t, t, 1.f));
-    const float s = c * t;
-    wr = s * (zr * rz);
-    wi = s * (zi * rz);  // w = s e^{i phi}
-    taz = t * az;        // norm transfer: a' = a - t|z|, b' = b + t|z|
+    const float d = 0.5f * (b - a);
+    const float q = fmaf(d, d, zz);
+    const float h = q * rsqrtf(q);
+    const float g = __fdividef(1.f, fabsf(d) + h);
+    const float zg = zz * g;
+    c = rsqrt_unit(fmaf(zg, g, 1.f));
+    const float sg = copysignf(c * g, d);
+    wr = zr * sg;
+    wi = zi * sg;
+    taz = copysignf(zg, d);  // norm transfer: a' = a - t|z|, b' = b + t|z|
+}
+
+// sum zr and zi over the warp with 7 shuffles instead of 10: the first butterfly step leaves the zr partial sums in the
+// lower half-warp and the zi partial sums in the upper one
+__device__ __forceinline__ void warp_sum2(float& zr, float& zi, int lane) {
+    const bool hi = lane & 16;
+    const float send = hi ? zr : zi;
+    float v = (hi ? zi : zr) + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    zr = __shfl_sync(0xffffffffu, v, 0);
+    zi = __shfl_sync(0xffffffffu, v, 16);
 }
 
 // Rotate the pair (X, Y) of shared-memory vectors so that X^H Y = 0. Returns |X^H Y|^2 / (|X|^2 |Y|^2).
@@ -61,8 +83,7 @@ __device__ __forceinline__ float rotate_pair(float2* __restrict__ X, float2* __r
         zi = fmaf(x.x, y.y, zi);
         zi = fmaf(-x.y, y.x, zi);
     }
-    zr = warp_sum(zr);
-    zi = warp_sum(zi);
+    warp_sum2(zr, zi, lane);
     const float a = *nx, b = *ny;
     __syncwarp();  // every lane has read the cached norms before lane 0 rewrites them below
     const float zz = zr * zr + zi * zi;
@@ -211,33 +232,44 @@ jacobi_pairs_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int ldot,
 // the bsz vectors of block J (shared memory) one per round, (w + q) mod bsz, so no two warps touch the same y. Per pair
 // shared memory is read once and written once (the generic kernel above moves each vector three times). Gram path
 // only (ldot == ltot == r <= 32 * EPL).
+//
+// Data layout inside the kernel is PLANAR and pair-packed: a lane owns element pairs (t, t+1), t = 2*lane + 64*p, and
+// holds (re_t, re_t+1) and (im_t, im_t+1) as float2 registers; block J sits in shared memory as separate re / im
+// planes. Every dot product and rotation is then a packed fma.rn.f32x2 (FFMA2) with no operand shuffling:
+// 4 FFMA2 per element pair for the inner product, 12 for the rotation (the interleaved form needs 32 scalar FMAs).
 template <int EPL>
 __global__ void __launch_bounds__(512, (EPL <= 8) ? 2 : 1)
 jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, int bsz, int nb, int round,
                     float tol2_rot, unsigned* __restrict__ offmax, const int32_t* __restrict__ done) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(EPL % 2 == 0, "element pairs");
     constexpr int L = 32 * EPL;
+    constexpr int NP = EPL / 2;
     const int npairs = nb >> 1;
     const int b = blockIdx.x / npairs;
     const int pslot = blockIdx.x - b * npairs;
     if (done[b]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* Y = reinterpret_cast<float2*>(smem_raw);          // [bsz][L]
-    float* nrm = reinterpret_cast<float*>(Y + (size_t)bsz * L);  // [bsz]
-    int* gidx = reinterpret_cast<int*>(nrm + bsz);             // [bsz]
+    float* YR = reinterpret_cast<float*>(smem_raw);   // [bsz][L]
+    float* YI = YR + (size_t)bsz * L;                  // [bsz][L]
+    float* nrm = YI + (size_t)bsz * L;                 // [bsz]
+    int* gidx = reinterpret_cast<int*>(nrm + bsz);     // [bsz]
     int bi, bj;
     rr_pair(nb, round, pslot, bi, bj);
     float2* Wb = W + (size_t)b * mat_stride;
 
     const int gx = bi * bsz + warp;
     const bool validx = gx < r;
-    float2 x[EPL];
+    float2 xr[NP], xi[NP];
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-        const int t = lane + 32 * e;
-        x[e] = (validx && t < r) ? Wb[(size_t)gx * ld + t] : make_float2(0.f, 0.f);
-        a = fmaf(x[e].x, x[e].x, fmaf(x[e].y, x[e].y, a));
+    for (int p = 0; p < NP; ++p) {
+        const int t = 2 * lane + 64 * p;
+        const float2 g0 = (validx && t < r) ? Wb[(size_t)gx * ld + t] : make_float2(0.f, 0.f);
+        const float2 g1 = (validx && t + 1 < r) ? Wb[(size_t)gx * ld + t + 1] : make_float2(0.f, 0.f);
+        xr[p] = make_float2(g0.x, g1.x);
+        xi[p] = make_float2(g0.y, g1.y);
+        a += g0.x * g0.x + g0.y * g0.y + g1.x * g1.x + g1.y * g1.y;
     }
     a = warp_sum(a);
     {
@@ -245,11 +277,13 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
         const bool validy = gy < r;
         float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-            const int t = lane + 32 * e;
-            const float2 v = (validy && t < r) ? Wb[(size_t)gy * ld + t] : make_float2(0.f, 0.f);
-            Y[(size_t)warp * L + t] = v;
-            s = fmaf(v.x, v.x, fmaf(v.y, v.y, s));
+        for (int p = 0; p < NP; ++p) {
+            const int t = 2 * lane + 64 * p;
+            const float2 g0 = (validy && t < r) ? Wb[(size_t)gy * ld + t] : make_float2(0.f, 0.f);
+            const float2 g1 = (validy && t + 1 < r) ? Wb[(size_t)gy * ld + t + 1] : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(YR + (size_t)warp * L + t) = make_float2(g0.x, g1.x);
+            *reinterpret_cast<float2*>(YI + (size_t)warp * L + t) = make_float2(g0.y, g1.y);
+            s += g0.x * g0.x + g0.y * g0.y + g1.x * g1.x + g1.y * g1.y;
         }
         s = warp_sum(s);
         if (lane == 0) {
@@ -264,19 +298,21 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
         int j = warp + q;
         if (j >= bsz) j -= bsz;
         if (validx && gidx[j] >= 0) {
-            float2* Yj = Y + (size_t)j * L;
-            float2 y[EPL];
-            float zr = 0.f, zi = 0.f;
+            float* yrp = YR + (size_t)j * L + 2 * lane;
+            float* yip = YI + (size_t)j * L + 2 * lane;
+            float2 yr[NP], yi[NP];
+            float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f), R = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) {
-                y[e] = Yj[lane + 32 * e];
-                zr = fmaf(x[e].x, y[e].x, zr);
-                zr = fmaf(x[e].y, y[e].y, zr);
-                zi = fmaf(x[e].x, y[e].y, zi);
-                zi = fmaf(-x[e].y, y[e].x, zi);
+            for (int p = 0; p < NP; ++p) {
+                yr[p] = *reinterpret_cast<const float2*>(yrp + 64 * p);
+                yi[p] = *reinterpret_cast<const float2*>(yip + 64 * p);
+                P = __ffma2_rn(xr[p], yr[p], P);  // z = x^H y : re = xr yr + xi yi ; im = xr yi - xi yr
+                P = __ffma2_rn(xi[p], yi[p], P);
+                Q = __ffma2_rn(xr[p], yi[p], Q);
+                R = __ffma2_rn(xi[p], yr[p], R);
             }
-            zr = warp_sum(zr);
-            zi = warp_sum(zi);
+            float zr = P.x + P.y, zi = (Q.x + Q.y) - (R.x + R.y);
+            warp_sum2(zr, zi, lane);
             const float bn = nrm[j];
             const float zz = zr * zr + zi * zi;
             float rel2 = 0.f;
@@ -285,15 +321,19 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
             if (rel2 > tol2_rot && zz > 0.f) {
                 float c, wr, wi, taz;
                 rotation_params(a, bn, zr, zi, zz, c, wr, wi, taz);
+                const float2 cc = make_float2(c, c), pwr = make_float2(wr, wr), nwr = make_float2(-wr, -wr),
+                             pwi = make_float2(wi, wi), nwi = make_float2(-wi, -wi);
 #pragma unroll
-                for (int e = 0; e < EPL; ++e) {
-                    const float2 xo = x[e], yo = y[e];
-                    float2 yn;
-                    x[e].x = fmaf(c, xo.x, -(wr * yo.x + wi * yo.y));
-                    x[e].y = fmaf(c, xo.y, -(wr * yo.y - wi * yo.x));
-                    yn.x = fmaf(c, yo.x, wr * xo.x - wi * xo.y);
-                    yn.y = fmaf(c, yo.y, wr * xo.y + wi * xo.x);
-                    Yj[lane + 32 * e] = yn;
+                for (int p = 0; p < NP; ++p) {
+                    // x' = c x - conj(w) y ; y' = w x + c y
+                    const float2 nxr = __ffma2_rn(cc, xr[p], __ffma2_rn(nwr, yr[p], __fmul2_rn(nwi, yi[p])));
+                    const float2 nxi = __ffma2_rn(cc, xi[p], __ffma2_rn(nwr, yi[p], __fmul2_rn(pwi, yr[p])));
+                    const float2 nyr = __ffma2_rn(cc, yr[p], __ffma2_rn(pwr, xr[p], __fmul2_rn(nwi, xi[p])));
+                    const float2 nyi = __ffma2_rn(cc, yi[p], __ffma2_rn(pwr, xi[p], __fmul2_rn(pwi, xr[p])));
+                    xr[p] = nxr;
+                    xi[p] = nxi;
+                    *reinterpret_cast<float2*>(yrp + 64 * p) = nyr;
+                    *reinterpret_cast<float2*>(yip + 64 * p) = nyi;
                 }
                 a = fmaxf(a - taz, 0.f);
                 if (lane == 0) nrm[j] = fmaxf(bn + taz, 0.f);
@@ -304,18 +344,22 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
 
     if (validx) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-            const int t = lane + 32 * e;
-            if (t < r) Wb[(size_t)gx * ld + t] = x[e];
+        for (int p = 0; p < NP; ++p) {
+            const int t = 2 * lane + 64 * p;
+            if (t < r) Wb[(size_t)gx * ld + t] = make_float2(xr[p].x, xi[p].x);
+            if (t + 1 < r) Wb[(size_t)gx * ld + t + 1] = make_float2(xr[p].y, xi[p].y);
         }
     }
     {
         const int gy = gidx[warp];
         if (gy >= 0) {
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) {
-                const int t = lane + 32 * e;
-                if (t < r) Wb[(size_t)gy * ld + t] = Y[(size_t)warp * L + t];
+            for (int p = 0; p < NP; ++p) {
+                const int t = 2 * lane + 64 * p;
+                const float2 vr = *reinterpret_cast<const float2*>(YR + (size_t)warp * L + t);
+                const float2 vi = *reinterpret_cast<const float2*>(YI + (size_t)warp * L + t);
+                if (t < r) Wb[(size_t)gy * ld + t] = make_float2(vr.x, vi.x);
+                if (t + 1 < r) Wb[(size_t)gy * ld + t + 1] = make_float2(vr.y, vi.y);
             }
         }
     }
@@ -338,7 +382,7 @@ int launch_cross(vk_context* h, float2* W, size_t mat_stride, const JacobiPlan& 
 int cross_epl(const JacobiPlan& p) {
     if (p.ldot != p.ltot || p.ltot != p.r || p.nb <= 2 || p.bsz != 16) return 0;
     const int need = (p.r + 31) / 32;
-    const int opts[] = {3, 4, 6, 8, 12, 16};
+    const int opts[] = {4, 6, 8, 12, 16};
     for (int e : opts)
         if (need <= e) return e;
     return 0;
@@ -347,7 +391,6 @@ int cross_epl(const JacobiPlan& p) {
 int launch_cross_dispatch(vk_context* h, int epl, float2* W, size_t mat_stride, const JacobiPlan& p, int round,
                           unsigned nblocks, float tol2_rot, unsigned* offmax, const int32_t* done) {
     switch (epl) {
-        case 3: return launch_cross<3>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
         case 4: return launch_cross<4>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
         case 6: return launch_cross<6>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
         case 8: return launch_cross<8>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);

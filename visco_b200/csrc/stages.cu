@@ -470,6 +470,79 @@ struct ReconOp {  // out[t][v] = sum_c (U[t][c] S[c]) Vt[c][v]
     __device__ void reduce_add(int, int, float) const {}
 };
 
+// Rank-k reconstruction for small k (north_star item (d)): out[t][v] = sum_c (U[t][c] S[c]) Vt[c][v], k <= KC <= 8.
+// HBM-bound by the output stream, so everything else is arranged around 128-bit coalesced streaming stores:
+//   * a thread owns two adjacent channels (one float4 of output per row) and keeps its Vt[c][v0..v0+1] values, plus
+//     their (im, re) swapped twins, in registers for the whole row loop;
+//   * U*S for the CTA's rows sits in shared memory pre-expanded as (ar, ar, -ai, ai), so one complex MAC is two packed
+//     fma.rn.f32x2 (FFMA2): acc += (ar, ar) * (br, bi) + (-ai, ai) * (bi, br);
+//   * rows are split across CTAs (ROWS per CTA) so a small batch still fills 148 SMs.
+template <int KC, int ROWS>
+__global__ void __launch_bounds__(128)
+recon_smallk_kernel(const float2* __restrict__ U, const float* __restrict__ S, const float2* __restrict__ Vt,
+                    float2* __restrict__ out, int m, int n, int kmax, int strips, int rsplit) {
+    __shared__ float4 us[ROWS * KC];
+    int bid = blockIdx.x;
+    const int rs = bid % rsplit;
+    bid /= rsplit;
+    const int strip = bid % strips;
+    const int b = bid / strips;
+    const int t0 = rs * ROWS;
+    const int rows = min(ROWS, m - t0);
+    for (int e = threadIdx.x; e < rows * KC; e += 128) {
+        const int t = e / KC, c = e - t * KC;
+        float2 u = make_float2(0.f, 0.f);
+        float s = 0.f;
+        if (c < kmax) {
+            u = U[((size_t)b * m + t0 + t) * kmax + c];
+            s = S[(size_t)b * kmax + c];
+        }
+        us[e] = make_float4(u.x * s, u.x * s, -u.y * s, u.y * s);
+    }
+    const int v0 = strip * 256 + threadIdx.x * 2;
+    const bool live = v0 < n;  // n is even on this path, so v0 + 1 < n too
+    float2 va[KC], vas[KC], vb[KC], vbs[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && c < kmax) v = *reinterpret_cast<const float4*>(Vt + ((size_t)b * kmax + c) * n + v0);
+        va[c] = make_float2(v.x, v.y);
+        vas[c] = make_float2(v.y, v.x);
+        vb[c] = make_float2(v.z, v.w);
+        vbs[c] = make_float2(v.w, v.z);
+    }
+    __syncthreads();
+    if (!live) return;
+    float2* o = out + ((size_t)b * m + t0) * n + v0;
+#pragma unroll 4
+    for (int t = 0; t < rows; ++t) {
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            const float4 a = us[t * KC + c];
+            const float2 aa = make_float2(a.x, a.y), ab = make_float2(a.z, a.w);
+            acc0 = __ffma2_rn(aa, va[c], acc0);
+            acc0 = __ffma2_rn(ab, vas[c], acc0);
+            acc1 = __ffma2_rn(aa, vb[c], acc1);
+            acc1 = __ffma2_rn(ab, vbs[c], acc1);
+        }
+        __stcs(reinterpret_cast<float4*>(o + (size_t)t * n), make_float4(acc0.x, acc0.y, acc1.x, acc1.y));
+    }
+}
+
+template <int KC>
+static int launch_recon_smallk(vk_context* h, const float2* U, const float* S, const float2* Vt, int B, int m, int n,
+                               int kmax, float2* out) {
+    constexpr int ROWS = 64;
+    const int strips = (n + 255) / 256;
+    const int rsplit = (m + ROWS - 1) / ROWS;
+    const long long nblocks = (long long)B * strips * rsplit;
+    if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "reconstruct: grid too large");
+    recon_smallk_kernel<KC, ROWS><<<(unsigned)nblocks, 128, 0, h->stream>>>(U, S, Vt, out, m, n, kmax, strips, rsplit);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 // =================================================================================================================
 // Synthetic MeerKAT-like visibilities
 // =================================================================================================================
@@ -664,6 +737,13 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
 
 int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
                           int m, int n, int kmax, float2* out) {
+    // small rank: dedicated streaming kernel (factors are zero-padded beyond ranks[b], so kmax modes are summed)
+    const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    if (aligned && kmax <= 8 && !h->recon_generic) {
+        if (kmax <= 2) return launch_recon_smallk<2>(h, U, S, Vt, B, m, n, kmax, out);
+        if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, B, m, n, kmax, out);
+        return launch_recon_smallk<8>(h, U, S, Vt, B, m, n, kmax, out);
+    }
     ReconOp op{U, S, Vt, ranks, out, m, n, kmax};
     return cgemm_launch<64, 64, 4, 4, 8>(h, op, B);
 }
