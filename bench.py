@@ -256,13 +256,8 @@ def run_ours(args):
 
     log('gather')
     # ---- the only collective: gather per-matrix ranks + statistics (after the timed region) ----
-    rk, st = fac[3], fac[4]
-    if world > 1:
-        rk_all = [torch.empty_like(rk) for _ in range(world)]
-        st_all = [torch.empty_like(st) for _ in range(world)]
-        dist.all_gather(rk_all, rk)
-        dist.all_gather(st_all, st)
-        rk, st = torch.cat(rk_all), torch.cat(st_all)
+    from visco_b200.shard import gather_ranks_stats
+    rk, st = gather_ranks_stats(fac[3], fac[4])
     rk_h, st_h = rk.cpu().numpy(), st.cpu().numpy()
     kbar = float(rk_h.mean())
 
