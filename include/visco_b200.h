@@ -54,10 +54,11 @@ const char* vk_version(void);
 /* cudaStream_t passed as void*; NULL = the legacy default stream. */
 int vk_set_stream(vk_handle h, void* cuda_stream);
 int vk_sync(vk_handle h);
-/* options: "jacobi_tol" (relative off-diagonal stop level, default 1e-6), "max_sweeps" (default 30),
+/* options: "jacobi_tol" (relative off-diagonal stop level, default 1e-4: a sweep that met nothing larger ends the
+ *          iteration; its own rotations leave the vectors orthogonal at the float32 noise floor), "max_sweeps" (default 30),
  *          "gram_impl" (0 = auto: tcgen05 where the shape allows, 1 = force SIMT fp32, 2 = force tcgen05),
  *          "check_finite" (default 1), "check_every" (host convergence poll period in sweeps, default 1),
- *          "jacobi_bsz" (vectors per block, 0 = auto), "chunk" (matrices per internal pass, 0 = auto),
+ *          "jacobi_bsz" (vectors per block, 0 = auto), "jacobi_groups" (concurrent matrix groups, 0 = auto), "chunk" (matrices per internal pass, 0 = auto),
  *          "stage_timing" (0/1, see vk_last_stage_ms). */
 int vk_set_option(vk_handle h, const char* key, double value);
 /* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own

@@ -206,6 +206,11 @@ int vk_destroy(vk_handle h) {
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& s : h->sub)
+        if (s) cudaStreamDestroy(s);
+    for (auto& e : h->sub_ev)
+        if (e) cudaEventDestroy(e);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     delete h;
     return VK_OK;
 }
@@ -238,6 +243,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->check_finite = (int)v;
     else if (k == "check_every")
         h->check_every = (int)v;
+    else if (k == "jacobi_groups")
+        h->jacobi_groups = (int)v;
     else if (k == "jacobi_bsz")
         h->jacobi_bsz = (int)v;
     else if (k == "stage_timing")

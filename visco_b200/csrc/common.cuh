@@ -8,6 +8,7 @@
 
 #define VK_SMEM_BUDGET (200 * 1024)  // dynamic shared memory we allow one CTA to ask for
 #define VK_MAX_R 2048                // largest min(m, n) the selection kernel sorts
+#define VK_MAX_GROUPS 4              // independent matrix groups (streams) the Jacobi driver overlaps
 
 struct vk_context {
     int device = 0;
@@ -21,12 +22,16 @@ struct vk_context {
     int64_t launches = 0;
     int num_sms = 148;
     // options
-    float jacobi_tol = 1e-6f;
+    float jacobi_tol = 1e-4f;  // sweep-level stop: every off-diagonal met in the sweep was below this (then rotated)
     int max_sweeps = 30;
     int gram_impl = 0;
     int check_finite = 1;
     int check_every = 1;
     int jacobi_bsz = 0;  // 0 = auto
+    int jacobi_groups = 0;  // 0 = auto
+    cudaStream_t sub[VK_MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t sub_ev[VK_MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)

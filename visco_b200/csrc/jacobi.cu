@@ -454,7 +454,7 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
     // was below max(user tol, 4 * noise) — the rotations of that sweep then leave the matrix at the noise floor.
     const float noise = sqrtf((float)p.ldot) * 5.9604645e-8f;
     const float tol_stop = fmaxf(h->jacobi_tol, 4.f * noise);
-    const float tol_rot = fmaxf(0.1f * h->jacobi_tol, noise);
+    const float tol_rot = noise;  // the rotation threshold never follows the (looser) stop level
     const float tol2_stop = tol_stop * tol_stop;
     const float tol2_rot = tol_rot * tol_rot;
     const size_t mat_stride = (size_t)p.r * p.ld;
@@ -469,34 +469,96 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
         return VK_OK;
     }
     const int epl = (h->jacobi_generic ? 0 : cross_epl(p));
-    for (int sweep = 0; sweep < h->max_sweeps; ++sweep) {
+    const int npairs = p.nb / 2;
+
+    // One launch covers B * npairs CTAs, usually a non-integer number of waves (KAT-7: 896 CTAs on 296 slots = 3.03
+    // waves, i.e. a 4th, almost empty wave per launch). The matrices are therefore split into G independent groups,
+    // each with its own stream: a group's launches stay ordered, different groups overlap, and no launch boundary
+    // drains the whole GPU. Each group always has exactly one sweep in flight; the host polls a group's convergence
+    // word while the other groups keep the SMs busy.
+    const int slots = h->num_sms * ((epl && epl <= 8) ? 2 : 1);
+    int G = h->jacobi_groups > 0 ? h->jacobi_groups : (int)(nblocks / (slots > 0 ? slots : 1));
+    if (G > VK_MAX_GROUPS) G = VK_MAX_GROUPS;
+    if (G > B) G = B;
+    if (G < 1) G = 1;
+    cudaStream_t gs[VK_MAX_GROUPS];
+    int gb0[VK_MAX_GROUPS + 1];
+    for (int g = 0; g <= G; ++g) gb0[g] = (int)((long long)B * g / G);
+    if (G > 1) {
+        for (int g = 0; g < G; ++g) {
+            if (!h->sub[g]) VK_CUDA(h, cudaStreamCreateWithFlags(&h->sub[g], cudaStreamNonBlocking));
+            if (!h->sub_ev[g]) VK_CUDA(h, cudaEventCreateWithFlags(&h->sub_ev[g], cudaEventDisableTiming));
+            gs[g] = h->sub[g];
+        }
+        if (!h->fork_ev) VK_CUDA(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        VK_CUDA(h, cudaEventRecord(h->fork_ev, st));
+        for (int g = 0; g < G; ++g) VK_CUDA(h, cudaStreamWaitEvent(gs[g], h->fork_ev, 0));
+    } else {
+        gs[0] = st;
+    }
+
+    auto issue_sweep = [&](int g) -> int {
+        const int b0 = gb0[g], nbg = gb0[g + 1] - gb0[g];
+        cudaStream_t sg = gs[g];
+        float2* Wg = W + (size_t)b0 * mat_stride;
+        const unsigned nblk = (unsigned)((long long)nbg * npairs);
         if (epl) {
             // pairs inside each block (generic kernel, intra-only), then every block pair with the register kernel
-            jacobi_pairs_kernel<<<(unsigned)nblocks, threads, p.smem, st>>>(W, mat_stride, p.ld, p.ldot, p.ltot, p.r,
-                                                                             p.bsz, p.nb, 0, 2, 1, tol2_rot, tol2_stop,
-                                                                             offmax_dev, done_dev, sweeps_dev);
+            jacobi_pairs_kernel<<<nblk, threads, p.smem, sg>>>(Wg, mat_stride, p.ld, p.ldot, p.ltot, p.r, p.bsz, p.nb, 0, 2,
+                                                                1, tol2_rot, tol2_stop, offmax_dev + b0, done_dev + b0,
+                                                                sweeps_dev + b0);
             VK_LAUNCH_CHECK(h);
             for (int round = 0; round < p.nb - 1; ++round) {
-                int rc = launch_cross_dispatch(h, epl, W, mat_stride, p, round, (unsigned)nblocks, tol2_rot, offmax_dev,
-                                               done_dev);
+                cudaStream_t keep = h->stream;
+                h->stream = sg;
+                const int rc = launch_cross_dispatch(h, epl, Wg, mat_stride, p, round, nblk, tol2_rot, offmax_dev + b0,
+                                                     done_dev + b0);
+                h->stream = keep;
                 if (rc) return rc;
             }
         } else {
             for (int round = 0; round < p.nb - 1; ++round) {
-                jacobi_pairs_kernel<<<(unsigned)nblocks, threads, p.smem, st>>>(
-                    W, mat_stride, p.ld, p.ldot, p.ltot, p.r, p.bsz, p.nb, round, round == 0 ? 1 : 0, 1, tol2_rot,
-                    tol2_stop, offmax_dev, done_dev, sweeps_dev);
+                jacobi_pairs_kernel<<<nblk, threads, p.smem, sg>>>(Wg, mat_stride, p.ld, p.ldot, p.ltot, p.r, p.bsz, p.nb,
+                                                                    round, round == 0 ? 1 : 0, 1, tol2_rot, tol2_stop,
+                                                                    offmax_dev + b0, done_dev + b0, sweeps_dev + b0);
                 VK_LAUNCH_CHECK(h);
             }
         }
-        VK_CUDA(h, cudaMemsetAsync(active_dev, 0, sizeof(int32_t), st));
-        sweep_check_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, tol2_stop, offmax_dev, done_dev, sweeps_dev, active_dev);
+        VK_CUDA(h, cudaMemsetAsync(active_dev + 16 * g, 0, sizeof(int32_t), sg));
+        sweep_check_kernel<<<(nbg + 255) / 256, 256, 0, sg>>>(nbg, tol2_stop, offmax_dev + b0, done_dev + b0,
+                                                              sweeps_dev + b0, active_dev + 16 * g);
         VK_LAUNCH_CHECK(h);
-        const bool poll = ((sweep + 1) % (h->check_every > 0 ? h->check_every : 1) == 0) || sweep + 1 == h->max_sweeps;
-        if (poll) {
-            VK_CUDA(h, cudaMemcpyAsync(h->h_poll, active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-            VK_CUDA(h, cudaStreamSynchronize(st));
-            if (h->h_poll[0] == 0) break;
+        VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 8 + g, active_dev + 16 * g, sizeof(int32_t), cudaMemcpyDeviceToHost, sg));
+        return VK_OK;
+    };
+
+    int issued[VK_MAX_GROUPS];
+    bool alive[VK_MAX_GROUPS];
+    int nalive = G;
+    for (int g = 0; g < G; ++g) {
+        alive[g] = true;
+        issued[g] = 1;
+        const int rc = issue_sweep(g);
+        if (rc) return rc;
+    }
+    while (nalive > 0) {
+        for (int g = 0; g < G; ++g) {
+            if (!alive[g]) continue;
+            VK_CUDA(h, cudaStreamSynchronize(gs[g]));
+            if (h->h_poll[8 + g] == 0 || issued[g] >= h->max_sweeps) {
+                alive[g] = false;
+                --nalive;
+                continue;
+            }
+            ++issued[g];
+            const int rc = issue_sweep(g);
+            if (rc) return rc;
+        }
+    }
+    if (G > 1) {
+        for (int g = 0; g < G; ++g) {
+            VK_CUDA(h, cudaEventRecord(h->sub_ev[g], gs[g]));
+            VK_CUDA(h, cudaStreamWaitEvent(st, h->sub_ev[g], 0));
         }
     }
     return VK_OK;
