@@ -45,7 +45,11 @@ def run(eng, nbl, ncorr, m, n, reps=3, **kw):
 
 if __name__ == "__main__":
     eng = get_engine(0)
-    print(torch.cuda.get_device_name(0), flush=True)
+    import os
+    for kv in filter(None, os.environ.get("VISCO_OPTS", "").split(",")):
+        k_, v_ = kv.split("=")
+        eng.set_option(k_, float(v_))
+    print(torch.cuda.get_device_name(0), os.environ.get("VISCO_OPTS", ""), flush=True)
     which = sys.argv[1:] or ["c2", "c4", "c3s", "c1"]
     t = time.time()
     if "c2" in which:

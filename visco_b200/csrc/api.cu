@@ -19,17 +19,18 @@ bool small_path(int m, int n) {
     return (size_t)(r + (r & 1)) * (size_t)(L + r) * sizeof(float2) + 1024 <= VK_SMEM_BUDGET;
 }
 
-WsLayout ws_layout(int chunk, int m, int n, int kmax) {
+WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0) {
+    if (gchunk < chunk) gchunk = chunk;
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
     WsLayout w;
     size_t off = 0;
-    const size_t wbytes = small_path(m, n) ? (size_t)chunk * r * (L + r) * sizeof(float2)
-                                           : (size_t)chunk * r * r * sizeof(float2);
+    const size_t wbytes = small_path(m, n) ? (size_t)gchunk * r * (L + r) * sizeof(float2)
+                                           : (size_t)gchunk * r * r * sizeof(float2);
     w.W = off, off += align_up(wbytes);
     w.perm = off, off += align_up((size_t)chunk * r * 4);
     w.inv = off, off += align_up((size_t)chunk * r * 4);
-    w.gscale = off, off += align_up((size_t)chunk * 4);
+    w.gscale = off, off += align_up((size_t)gchunk * 4);
     w.sweeps = off, off += align_up((size_t)chunk * 4);
     w.done = off, off += align_up((size_t)chunk * 4);
     w.offmax = off, off += align_up((size_t)chunk * 4);
@@ -50,6 +51,19 @@ int auto_chunk(const vk_context* h, int B, int m, int n) {
     if (c < 32) c = 32;
     if (c > (size_t)B) c = B;
     return (int)c;
+}
+
+// The Gram product is launched over a super-chunk of several Jacobi chunks: one launch then covers many waves of
+// tiles (a 32-matrix chunk of 512 x 4096 matrices is only 2.2 waves of 148 CTAs, a 28 % quantisation loss).
+int gram_chunk(int B, int chunk, int m, int n) {
+    if (small_path(m, n)) return chunk;
+    const int r = m < n ? m : n;
+    size_t cap = (512u << 20) / ((size_t)r * r * 8);  // at most 512 MB of Gram matrices at a time
+    if (cap < 1) cap = 1;
+    int g = chunk;
+    while (g < 128 && (size_t)(g + chunk) <= cap) g += chunk;
+    if (g > B) g = B < chunk ? chunk : ((B + chunk - 1) / chunk) * chunk;
+    return g;
 }
 
 int ensure(vk_context* h, void** p, size_t* have, size_t need) {
@@ -84,14 +98,31 @@ struct StageTimer {
     }
 };
 
-int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
-                   float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L) {
+int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale, int32_t* nonfinite) {
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
-    float2* W = reinterpret_cast<float2*>(ws + L.W);
+    int rc;
+    const bool tc = (h->gram_impl == 2) || (h->gram_impl == 0 && vk_gram_tc_supported(m, n, side));
+    if (tc) {
+        if (!vk_gram_tc_supported(m, n, side))
+            return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape");
+        if ((rc = vk_launch_gram_tc(h, A, B, m, n, W))) return rc;
+    } else {
+        if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;
+    }
+    return vk_launch_gram_normalise(h, W, B, r, gscale, nonfinite);
+}
+
+int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
+                   float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L,
+                   int sub0 = 0, bool gram_done = false) {
+    // sub0: index of this chunk's first matrix inside the Gram super-chunk (W and gscale are laid out per super-chunk)
+    const int r = m < n ? m : n;
+    const int side = m <= n ? 0 : 1;
+    float2* W = reinterpret_cast<float2*>(ws + L.W) + (small_path(m, n) ? 0 : (size_t)sub0 * r * r);
     int32_t* perm = reinterpret_cast<int32_t*>(ws + L.perm);
     float* inv = reinterpret_cast<float*>(ws + L.inv);
-    float* gscale = reinterpret_cast<float*>(ws + L.gscale);
+    float* gscale = reinterpret_cast<float*>(ws + L.gscale) + sub0;
     int32_t* sweeps = reinterpret_cast<int32_t*>(ws + L.sweeps);
     int32_t* done = reinterpret_cast<int32_t*>(ws + L.done);
     unsigned* offmax = reinterpret_cast<unsigned*>(ws + L.offmax);
@@ -100,7 +131,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
     float* norm2 = reinterpret_cast<float*>(ws + L.norm2);
     int rc;
     StageTimer tm(h);
-    VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
+    if (!gram_done) VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
     if (small_path(m, n)) {
         const int Llong = m < n ? n : m;
         const JacobiPlan p = vk_jacobi_plan(h, r, Llong, Llong + r);
@@ -120,15 +151,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
     } else {
         const JacobiPlan p = vk_jacobi_plan(h, r, r, r);
         tm.mark(0);
-        const bool tc = (h->gram_impl == 2) || (h->gram_impl == 0 && vk_gram_tc_supported(m, n, side));
-        if (tc) {
-            if (!vk_gram_tc_supported(m, n, side))
-                return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape");
-            if ((rc = vk_launch_gram_tc(h, A, B, m, n, W))) return rc;
-        } else {
-            if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;
-        }
-        if ((rc = vk_launch_gram_normalise(h, W, B, r, gscale, nonfinite))) return rc;
+        if (!gram_done && (rc = gram_stage(h, A, B, m, n, W, gscale, nonfinite))) return rc;
         tm.mark(1);
         if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active))) return rc;
         tm.mark(2);
@@ -264,7 +287,7 @@ size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax) {
     if (B <= 0 || m < 1 || n < 1 || kmax < 1) return 0;
     int chunk = (h && h->chunk > 0) ? h->chunk : auto_chunk(h, B, m, n);
     if (chunk > B) chunk = B;
-    return ws_layout(chunk, m, n, kmax).total;
+    return ws_layout(chunk, m, n, kmax, gram_chunk(B, chunk, m, n)).total;
 }
 
 int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(m, n)) ? 1 : 0; }
@@ -285,7 +308,8 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     VK_CUDA(h, cudaSetDevice(h->device));
     int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n);
     if (chunk > B) chunk = B;
-    const WsLayout L = ws_layout(chunk, m, n, kmax);
+    const int gchunk = gram_chunk(B, chunk, m, n);
+    const WsLayout L = ws_layout(chunk, m, n, kmax, gchunk);
     unsigned char* wsp = static_cast<unsigned char*>(ws);
     if (!wsp) {
         if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total))) return rc;
@@ -299,12 +323,29 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     const float2* Ap = static_cast<const float2*>(A);
     float2* Up = static_cast<float2*>(U);
     float2* Vp = static_cast<float2*>(Vt);
-    for (int b0 = 0; b0 < B; b0 += chunk) {
-        const int nb = (B - b0) < chunk ? (B - b0) : chunk;
-        rc = compress_chunk(h, Ap + (size_t)b0 * m * n, nb, m, n, fixed_rank, decorrelation, kmax,
-                            Up + (size_t)b0 * m * kmax, S + (size_t)b0 * kmax, Vp + (size_t)b0 * kmax * n, ranks + b0,
-                            stats + (size_t)b0 * 4, wsp, L);
-        if (rc) return rc;
+    const bool gram_path = !small_path(m, n);
+    for (int g0 = 0; g0 < B; g0 += gchunk) {
+        const int ng = (B - g0) < gchunk ? (B - g0) : gchunk;
+        if (gram_path) {
+            // Gram + normalisation for the whole super-chunk in one launch each
+            int32_t* nonfinite = reinterpret_cast<int32_t*>(wsp + L.nonfinite);
+            VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
+            StageTimer tg(h);
+            tg.mark(0);
+            rc = gram_stage(h, Ap + (size_t)g0 * m * n, ng, m, n, reinterpret_cast<float2*>(wsp + L.W),
+                            reinterpret_cast<float*>(wsp + L.gscale), nonfinite);
+            if (rc) return rc;
+            tg.mark(1);
+            tg.collect(0, 0, 1);
+        }
+        for (int s0 = 0; s0 < ng; s0 += chunk) {
+            const int nb = (ng - s0) < chunk ? (ng - s0) : chunk;
+            const int b0 = g0 + s0;
+            rc = compress_chunk(h, Ap + (size_t)b0 * m * n, nb, m, n, fixed_rank, decorrelation, kmax,
+                                Up + (size_t)b0 * m * kmax, S + (size_t)b0 * kmax, Vp + (size_t)b0 * kmax * n, ranks + b0,
+                                stats + (size_t)b0 * 4, wsp, L, s0, gram_path);
+            if (rc) return rc;
+        }
     }
     if (h->stage_timing) {
         cudaEventRecord(e1, h->stream);

@@ -367,6 +367,87 @@ struct FormVOp {  // Vt[c][v] = sum_t conj(W[perm c][t]) inv[c] * A[t][v]       
     __device__ void store(int b, int c, int j, float2 v) const { Vt[((size_t)b * kmax + c) * n + j] = v; }
     __device__ void reduce_add(int b, int c, float v) const { atomicAdd(&norm2[(size_t)b * kmax + c], v); }
 };
+// V-formation for small k (north_star item (c), wide matrices): Vt[c][v] = sum_t conj(u_c[t]) A[t][v] with k <= KC <= 8.
+// HBM-bound by the single read of A: a thread owns two adjacent channels, streams its float4 of every row of A
+// (128-bit loads, 8 rows in flight), and keeps KC x 2 complex accumulators in registers; the coefficients
+// conj(W[perm c][t]) * inv[c] sit in shared memory pre-expanded as (xr, xr, -xi, xi) so a complex MAC is two FFMA2.
+// The epilogue writes the unnormalised rows and accumulates their squared norms (the refined singular values).
+template <int KC>
+__global__ void __launch_bounds__(128)
+formv_smallk_kernel(const float2* __restrict__ A, const float2* __restrict__ W, const int32_t* __restrict__ perm,
+                    const float* __restrict__ inv, const int32_t* __restrict__ ranks, float2* __restrict__ Vt,
+                    float* __restrict__ norm2, int m, int n, int kmax, int strips) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* xs = reinterpret_cast<float4*>(smem_raw);  // [m][KC]
+    __shared__ float red[KC];
+    const int strip = blockIdx.x % strips;
+    const int b = blockIdx.x / strips;
+    const int k = min(ranks[b], kmax);
+    if (threadIdx.x < KC) red[threadIdx.x] = 0.f;
+    for (int e = threadIdx.x; e < m * KC; e += 128) {
+        const int c = e / m, t = e - c * m;  // t fastest: coalesced reads of the eigenvector rows
+        float2 x = make_float2(0.f, 0.f);
+        if (c < k) {
+            const int p = perm[(size_t)b * m + c];
+            const float f = inv[(size_t)b * m + c];
+            const float2 w = W[((size_t)b * m + p) * m + t];
+            x = make_float2(w.x * f, -w.y * f);  // conj(u_c[t])
+        }
+        xs[t * KC + c] = make_float4(x.x, x.x, -x.y, x.y);
+    }
+    __syncthreads();
+    const int v0 = strip * 256 + threadIdx.x * 2;
+    const bool live = v0 < n;
+    float2 acc0[KC], acc1[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc0[c] = acc1[c] = make_float2(0.f, 0.f);
+    if (live) {
+        const float2* a = A + (size_t)b * m * n + v0;
+#pragma unroll 8
+        for (int t = 0; t < m; ++t) {
+            const float4 av = __ldcs(reinterpret_cast<const float4*>(a + (size_t)t * n));
+            const float2 a0 = make_float2(av.x, av.y), a0s = make_float2(av.y, av.x);
+            const float2 a1 = make_float2(av.z, av.w), a1s = make_float2(av.w, av.z);
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                const float4 x = xs[t * KC + c];
+                const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+                acc0[c] = __ffma2_rn(xa, a0, acc0[c]);
+                acc0[c] = __ffma2_rn(xb, a0s, acc0[c]);
+                acc1[c] = __ffma2_rn(xa, a1, acc1[c]);
+                acc1[c] = __ffma2_rn(xb, a1s, acc1[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        if (c < kmax) {
+            const bool valid = c < k;
+            const float4 o = valid ? make_float4(acc0[c].x, acc0[c].y, acc1[c].x, acc1[c].y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) *reinterpret_cast<float4*>(Vt + ((size_t)b * kmax + c) * n + v0) = o;
+            float s = (valid && live) ? (o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w) : 0.f;
+            s = warp_sum(s);
+            if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&red[c], s);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < KC && threadIdx.x < k) atomicAdd(&norm2[(size_t)b * kmax + threadIdx.x], red[threadIdx.x]);
+}
+
+template <int KC>
+static int launch_formv_smallk(vk_context* h, const float2* A, const float2* W, const int32_t* perm, const float* inv,
+                               const int32_t* ranks, float2* Vt, float* norm2, int B, int m, int n, int kmax) {
+    const int strips = (n + 255) / 256;
+    const long long nblocks = (long long)B * strips;
+    if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "formV: grid too large");
+    const size_t smem = (size_t)m * KC * sizeof(float4);
+    if (smem > 48 * 1024)
+        VK_CUDA(h, cudaFuncSetAttribute(formv_smallk_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    formv_smallk_kernel<KC><<<(unsigned)nblocks, 128, smem, h->stream>>>(A, W, perm, inv, ranks, Vt, norm2, m, n, kmax, strips);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 struct FormUOp {  // U[t][c] = sum_j A[t][j] * W[perm c][j] inv[c]                    (tall, r = n)
     const float2* A;
     const float2* W;
@@ -695,7 +776,15 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
         const int r = m;
         if ((rc = launch_cols(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
         FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
-        if (kmax <= 8)
+        const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16 == 0);
+        if (aligned && kmax <= 8 && (size_t)m * 8 * sizeof(float4) <= VK_SMEM_BUDGET && !h->recon_generic) {
+            if (kmax <= 2)
+                rc = launch_formv_smallk<2>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
+            else if (kmax <= 4)
+                rc = launch_formv_smallk<4>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
+            else
+                rc = launch_formv_smallk<8>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
+        } else if (kmax <= 8)
             rc = cgemm_launch<8, 256, 8, 2, 16>(h, op, B);
         else if (kmax <= 32)
             rc = cgemm_launch<32, 128, 4, 4, 16>(h, op, B);
