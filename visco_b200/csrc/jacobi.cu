@@ -300,16 +300,23 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
         if (validx && gidx[j] >= 0) {
             float* yrp = YR + (size_t)j * L + 2 * lane;
             float* yip = YI + (size_t)j * L + 2 * lane;
-            float2 yr[NP], yi[NP];
+            // y stays in registers between the inner product and the rotation. (Re-reading it from shared memory to fit
+            // 2 CTAs/SM at EPL = 16 was measured: 64 registers with spills, Jacobi time 219 -> 383 ms. Rejected.)
+            constexpr bool KEEP_Y = true;
+            float2 yr[KEEP_Y ? NP : 1], yi[KEEP_Y ? NP : 1];
             float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f), R = make_float2(0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                yr[p] = *reinterpret_cast<const float2*>(yrp + 64 * p);
-                yi[p] = *reinterpret_cast<const float2*>(yip + 64 * p);
-                P = __ffma2_rn(xr[p], yr[p], P);  // z = x^H y : re = xr yr + xi yi ; im = xr yi - xi yr
-                P = __ffma2_rn(xi[p], yi[p], P);
-                Q = __ffma2_rn(xr[p], yi[p], Q);
-                R = __ffma2_rn(xi[p], yr[p], R);
+                const float2 vr = *reinterpret_cast<const float2*>(yrp + 64 * p);
+                const float2 vi = *reinterpret_cast<const float2*>(yip + 64 * p);
+                if (KEEP_Y) {
+                    yr[p] = vr;
+                    yi[p] = vi;
+                }
+                P = __ffma2_rn(xr[p], vr, P);  // z = x^H y : re = xr yr + xi yi ; im = xr yi - xi yr
+                P = __ffma2_rn(xi[p], vi, P);
+                Q = __ffma2_rn(xr[p], vi, Q);
+                R = __ffma2_rn(xi[p], vr, R);
             }
             float zr = P.x + P.y, zi = (Q.x + Q.y) - (R.x + R.y);
             warp_sum2(zr, zi, lane);
@@ -326,10 +333,12 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     // x' = c x - conj(w) y ; y' = w x + c y
-                    const float2 nxr = __ffma2_rn(cc, xr[p], __ffma2_rn(nwr, yr[p], __fmul2_rn(nwi, yi[p])));
-                    const float2 nxi = __ffma2_rn(cc, xi[p], __ffma2_rn(nwr, yi[p], __fmul2_rn(pwi, yr[p])));
-                    const float2 nyr = __ffma2_rn(cc, yr[p], __ffma2_rn(pwr, xr[p], __fmul2_rn(nwi, xi[p])));
-                    const float2 nyi = __ffma2_rn(cc, yi[p], __ffma2_rn(pwr, xi[p], __fmul2_rn(pwi, xr[p])));
+                    const float2 vr = KEEP_Y ? yr[p] : *reinterpret_cast<const float2*>(yrp + 64 * p);
+                    const float2 vi = KEEP_Y ? yi[p] : *reinterpret_cast<const float2*>(yip + 64 * p);
+                    const float2 nxr = __ffma2_rn(cc, xr[p], __ffma2_rn(nwr, vr, __fmul2_rn(nwi, vi)));
+                    const float2 nxi = __ffma2_rn(cc, xi[p], __ffma2_rn(nwr, vi, __fmul2_rn(pwi, vr)));
+                    const float2 nyr = __ffma2_rn(cc, vr, __ffma2_rn(pwr, xr[p], __fmul2_rn(nwi, xi[p])));
+                    const float2 nyi = __ffma2_rn(cc, vi, __ffma2_rn(pwr, xi[p], __fmul2_rn(pwi, xr[p])));
                     xr[p] = nxr;
                     xi[p] = nxi;
                     *reinterpret_cast<float2*>(yrp + 64 * p) = nyr;
@@ -400,6 +409,153 @@ int launch_cross_dispatch(vk_context* h, int epl, float2* W, size_t mat_stride, 
     return vk_fail(h, VK_EINVAL, "jacobi: no cross kernel for this size");
 }
 
+// Whole-problem-in-one-CTA Jacobi for small vector sets (r <= 64: the small-matrix SVD path and small Gram matrices).
+// A pair is handled by a GROUP of LPP lanes (LPP = 4..32), so a warp rotates 32/LPP pairs at once and the scalar
+// rotation parameters, the reductions and the loop overhead are shared by them; with one warp per pair and only four
+// elements per lane (64 x 64 matrices) that overhead was ~95 % of the instruction stream. Vectors live in shared
+// memory as separate re / im planes (rows padded by 8 floats to spread the groups over the banks); inner products and
+// rotations use packed fma.rn.f32x2 on element pairs. Sweeps iterate inside the kernel until convergence.
+template <int LPP>
+__global__ void __launch_bounds__(1024)
+jacobi_small_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int ldot, int ltot, int r, int nslots, int lpad,
+                    int max_sweeps, float tol2_rot, float tol2_stop, int32_t* __restrict__ done,
+                    int32_t* __restrict__ sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GPW = 32 / LPP;
+    float* XR = reinterpret_cast<float*>(smem_raw);      // [nslots][lpad]
+    float* XI = XR + (size_t)nslots * lpad;               // [nslots][lpad]
+    float* nrm = XI + (size_t)nslots * lpad;              // [nslots]
+    __shared__ unsigned cta_max;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane % LPP;
+    const int pslot = warp * GPW + lane / LPP;
+    const int npairs = nslots >> 1;
+    const bool act = pslot < npairs;
+    float2* Wb = W + (size_t)b * mat_stride;
+
+    for (int v = warp; v < nslots; v += nwarps) {
+        float s = 0.f;
+        for (int t = lane; t < lpad; t += 32) {
+            float2 w = make_float2(0.f, 0.f);
+            if (v < r && t < ltot) w = Wb[(size_t)v * ld + t];
+            XR[(size_t)v * lpad + t] = w.x;
+            XI[(size_t)v * lpad + t] = w.y;
+            if (t < ldot) s = fmaf(w.x, w.x, fmaf(w.y, w.y, s));
+        }
+        s = warp_sum(s);
+        if (lane == 0) nrm[v] = s;
+    }
+    if (threadIdx.x == 0) cta_max = 0u;
+    __syncthreads();
+
+    const int nd = act ? ldot : 0, nt = act ? ltot : 0;
+    int it = 0;
+    bool converged = false;
+    for (; it < max_sweeps; ++it) {
+        float mymax = 0.f;
+        for (int q = 0; q < nslots - 1; ++q) {
+            int s1 = 0, s2 = 1;
+            if (act) rr_pair(nslots, q, pslot, s1, s2);
+            float* xr = XR + (size_t)s1 * lpad;
+            float* xi = XI + (size_t)s1 * lpad;
+            float* yr = XR + (size_t)s2 * lpad;
+            float* yi = XI + (size_t)s2 * lpad;
+            float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f), R = make_float2(0.f, 0.f);
+            for (int e = 2 * g; e < nd; e += 2 * LPP) {
+                float2 a_r = *reinterpret_cast<const float2*>(xr + e), a_i = *reinterpret_cast<const float2*>(xi + e);
+                float2 b_r = *reinterpret_cast<const float2*>(yr + e), b_i = *reinterpret_cast<const float2*>(yi + e);
+                if (e + 1 >= nd) {  // odd ldot: the second element of the pair is not part of the inner product
+                    a_r.y = 0.f;
+                    a_i.y = 0.f;
+                }
+                P = __ffma2_rn(a_r, b_r, P);
+                P = __ffma2_rn(a_i, b_i, P);
+                Q = __ffma2_rn(a_r, b_i, Q);
+                R = __ffma2_rn(a_i, b_r, R);
+            }
+            float zr = P.x + P.y, zi = (Q.x + Q.y) - (R.x + R.y);
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1) {
+                zr += __shfl_xor_sync(0xffffffffu, zr, o);
+                zi += __shfl_xor_sync(0xffffffffu, zi, o);
+            }
+            const float an = nrm[s1], bn = nrm[s2];
+            __syncwarp();
+            const float zz = zr * zr + zi * zi;
+            float rel2 = 0.f;
+            if (act && an > 0.f && bn > 0.f) rel2 = __fdividef(zz, an * bn);
+            mymax = fmaxf(mymax, rel2);
+            if (rel2 > tol2_rot && zz > 0.f) {
+                float c, wr, wi, taz;
+                rotation_params(an, bn, zr, zi, zz, c, wr, wi, taz);
+                const float2 cc = make_float2(c, c), pwr = make_float2(wr, wr), nwr = make_float2(-wr, -wr),
+                             pwi = make_float2(wi, wi), nwi = make_float2(-wi, -wi);
+                for (int e = 2 * g; e < nt; e += 2 * LPP) {
+                    const float2 a_r = *reinterpret_cast<const float2*>(xr + e), a_i = *reinterpret_cast<const float2*>(xi + e);
+                    const float2 b_r = *reinterpret_cast<const float2*>(yr + e), b_i = *reinterpret_cast<const float2*>(yi + e);
+                    *reinterpret_cast<float2*>(xr + e) = __ffma2_rn(cc, a_r, __ffma2_rn(nwr, b_r, __fmul2_rn(nwi, b_i)));
+                    *reinterpret_cast<float2*>(xi + e) = __ffma2_rn(cc, a_i, __ffma2_rn(nwr, b_i, __fmul2_rn(pwi, b_r)));
+                    *reinterpret_cast<float2*>(yr + e) = __ffma2_rn(cc, b_r, __ffma2_rn(pwr, a_r, __fmul2_rn(nwi, a_i)));
+                    *reinterpret_cast<float2*>(yi + e) = __ffma2_rn(cc, b_i, __ffma2_rn(pwr, a_i, __fmul2_rn(pwi, a_r)));
+                }
+                if (g == 0) {
+                    nrm[s1] = fmaxf(an - taz, 0.f);
+                    nrm[s2] = fmaxf(bn + taz, 0.f);
+                }
+            }
+            __syncthreads();
+        }
+        mymax = warp_max(mymax);
+        if (lane == 0) atomicMax(&cta_max, __float_as_uint(mymax));
+        __syncthreads();
+        const float sweep_max = __uint_as_float(cta_max);
+        __syncthreads();
+        if (threadIdx.x == 0) cta_max = 0u;
+        // refresh the cached norms from the data once per sweep (they are updated by formula in between)
+        for (int v = warp; v < r; v += nwarps) {
+            float s = 0.f;
+            for (int t = lane; t < ldot; t += 32) {
+                const float a_ = XR[(size_t)v * lpad + t], b_ = XI[(size_t)v * lpad + t];
+                s = fmaf(a_, a_, fmaf(b_, b_, s));
+            }
+            s = warp_sum(s);
+            if (lane == 0) nrm[v] = s;
+        }
+        __syncthreads();
+        if (sweep_max <= tol2_stop) {
+            converged = true;
+            ++it;
+            break;
+        }
+    }
+    for (int v = warp; v < r; v += nwarps)
+        for (int t = lane; t < ltot; t += 32)
+            Wb[(size_t)v * ld + t] = make_float2(XR[(size_t)v * lpad + t], XI[(size_t)v * lpad + t]);
+    if (threadIdx.x == 0) {
+        sweeps[b] = it;
+        done[b] = converged ? 1 : 0;
+    }
+}
+
+template <int LPP>
+int launch_small(vk_context* h, float2* W, int B, const JacobiPlan& p, float tol2_rot, float tol2_stop, int32_t* done,
+                 int32_t* sweeps) {
+    const int nslots = p.r + (p.r & 1);
+    const int lpad = ((p.ltot + 1) / 2) * 2 + 8;
+    const int npairs = nslots / 2;
+    constexpr int GPW = 32 / LPP;
+    int warps = (npairs + GPW - 1) / GPW;
+    if (warps < 2) warps = 2;
+    const size_t smem = (size_t)nslots * lpad * 8 + (size_t)nslots * 4;
+    if (smem > 220 * 1024) return vk_fail(h, VK_EINVAL, "jacobi(small): problem does not fit shared memory");
+    VK_CUDA(h, cudaFuncSetAttribute(jacobi_small_kernel<LPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_small_kernel<LPP><<<B, 32 * warps, smem, h->stream>>>(W, (size_t)p.r * p.ld, p.ld, p.ldot, p.ltot, p.r, nslots,
+                                                                lpad, h->max_sweeps, tol2_rot, tol2_stop, done, sweeps);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 __global__ void sweep_check_kernel(int B, float tol2_stop, unsigned* __restrict__ offmax, int32_t* __restrict__ done,
                                    int32_t* __restrict__ sweeps, int32_t* __restrict__ active) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,6 +617,14 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
     const int threads = 32 * p.bsz;
     const long long nblocks = (long long)B * (p.nb / 2);
     if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "jacobi: batch too large");
+    if (p.nb == 2 && !h->jacobi_generic) {
+        // elements per lane ~ 8..16: lanes per pair from the vector length
+        const int want = (p.ltot + 15) / 16;
+        if (want <= 4) return launch_small<4>(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev);
+        if (want <= 8) return launch_small<8>(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev);
+        if (want <= 16) return launch_small<16>(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev);
+        return launch_small<32>(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev);
+    }
     if (p.nb == 2) {
         jacobi_pairs_kernel<<<(unsigned)nblocks, threads, p.smem, st>>>(W, mat_stride, p.ld, p.ldot, p.ltot, p.r, p.bsz,
                                                                          p.nb, 0, 1, h->max_sweeps, tol2_rot, tol2_stop,
