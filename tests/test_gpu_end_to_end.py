@@ -1,0 +1,88 @@
+"""GPU: the reference's own smoke configuration (tests/compression_tests.py:10-32 — XX,YY, decorrelation 0.90,
+batch_size 10, zstd level 3) through the drop-in drivers on the sample-MS bundle, checked against the oracle; plus
+cross-reading of leaf stores in both directions."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import visco_oracle as vo
+from visco_b200.msdata import VisData
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUNDLE = os.path.join(ROOT, "tests", "golden", "sample_ms_kat7.npz")
+KW = dict(consolidated=True, chunk_size_row=5000, overwrite=True, compressor="zstd", level=3, nworkers=1, nthreads=1,
+          memory_limit="2GB", direct_to_workers=False, fieldid=0, ddid=0, scan=1, column="DATA",
+          outcolumn="COMPRESSED_DATA", batch_size=10, dashboard_addr=None, host_addr=None)
+
+
+def _oracle_decompressed(vis, correlation, optimized, **rank):
+    out = np.zeros_like(vis.data)
+    corr_idx = {"XX": 0, "XY": 1, "YX": 2, "YY": 3}
+    for a1, a2 in vis.baselines():
+        rows = vis.baseline_rows(a1, a2)
+        blk = vis.data[rows]
+        if optimized:
+            for pair in (("XX", "YY"), ("XY", "YX")):
+                m = np.vstack([blk[:, :, corr_idx[pair[0]]], blk[:, :, corr_idx[pair[1]]]])
+                rec, _, _ = vo.roundtrip(m, **rank)
+                parts = vo.ref_unstack_vis(rec, len(rows))
+                out[rows, :, corr_idx[pair[0]]] = parts[0]
+                out[rows, :, corr_idx[pair[1]]] = parts[1]
+        else:
+            for c in correlation.split(","):
+                rec, _, _ = vo.roundtrip(blk[:, :, corr_idx[c]], **rank)
+                out[rows, :, corr_idx[c]] = rec
+    return out
+
+
+@pytest.mark.parametrize("correlation,optimized,rank", [
+    ("XX,YY", False, dict(decorrelation=0.90)),               # the reference's own test configuration
+    ("XX,XY,YX,YY", False, dict(compressionrank=2)),
+    ("XX,XY,YX,YY", True, dict(compressionrank=3)),           # --correlation-optimized: stacked leaves
+])
+def test_compress_decompress_sample_ms(tmp_path, correlation, optimized, rank):
+    from visco_b200.compress_ms import compress_full_ms
+    from visco_b200.decompress_ms import open_dataset, write_datasets_to_ms
+    from visco_b200.zarr_leaf import list_subtables, read_svd_from_zarr
+    vis = VisData.load(BUNDLE)
+    z = str(tmp_path / "store.zarr")
+    n = compress_full_ms(ms_path=BUNDLE, zarr_path=z, correlation=correlation, correlation_optimized=optimized, **KW, **rank)
+    assert n == 6
+    base = os.path.join(z, "MAIN", "COMPRESSED_DATA")
+    assert list_subtables(base) == ["ANT-0&ANT-1", "ANT-0&ANT-2", "ANT-0&ANT-3", "ANT-1&ANT-2", "ANT-1&ANT-3", "ANT-2&ANT-3"]
+    leaves = list_subtables(os.path.join(base, "ANT-0&ANT-1"))
+    assert leaves == (["diagonals", "offdiagonals"] if optimized else sorted(correlation.split(",")))
+    U, S, WT, rowid = read_svd_from_zarr(os.path.join(base, "ANT-1&ANT-3", leaves[0]))
+    assert U.shape[0] == (720 if optimized else 360) and WT.shape[1] == 16 and U.shape[1] == len(S) == WT.shape[0]
+    np.testing.assert_array_equal(rowid[:360], vis.rowid[vis.baseline_rows(1, 3)])
+    # decompress through the driver and through the bundle writer
+    out = open_dataset(z, "COMPRESSED_DATA", 7)
+    ms_out = write_datasets_to_ms(z, str(tmp_path / "decompressed.npz"), "COMPRESSED_DATA", 50)
+    np.testing.assert_array_equal(VisData.load(ms_out).data, out.data)
+    want = _oracle_decompressed(vis, correlation, optimized, **rank)
+    scale = np.abs(vis.data).max()
+    assert np.abs(out.data - want).max() <= 5e-5 * scale, np.abs(out.data - want).max() / scale
+    if not optimized and correlation == "XX,YY":
+        assert not out.data[:, :, 1].any() and not out.data[:, :, 2].any()      # uncompressed correlations stay zero
+
+
+def test_cross_reading_both_directions(tmp_path):
+    """Leaves written from the REFERENCE's factors (oracle = its restatement) are read and reconstructed by us; leaves
+    we write are reconstructed by the reference's arithmetic."""
+    from visco_b200.compress_ms import apply_svd
+    from visco_b200.decompress_ms import reconstruct_vis
+    from visco_b200.zarr_leaf import read_svd_from_zarr, write_svd_to_zarr
+    vis = VisData.load(BUNDLE)
+    a = vis.data[vis.baseline_rows(0, 2)][:, :, 0]
+    u, s, vt = vo.ref_apply_svd(a, compressionrank=4)
+    write_svd_to_zarr((u, s, vt), tmp_path / "ref_leaf", "zstd", 4, vis.rowid[vis.baseline_rows(0, 2)])
+    U, S, WT, _ = read_svd_from_zarr(tmp_path / "ref_leaf")
+    ours = reconstruct_vis(U, S, WT)
+    np.testing.assert_allclose(ours, vo.ref_reconstruct_vis(u, s, vt), atol=3e-5 * np.abs(a).max())
+    write_svd_to_zarr(apply_svd(a, compressionrank=4), tmp_path / "our_leaf", "gzip", 2, vis.rowid[vis.baseline_rows(0, 2)])
+    U, S, WT, _ = read_svd_from_zarr(tmp_path / "our_leaf")
+    theirs = vo.ref_reconstruct_vis(U, S, WT)
+    e_ref = np.linalg.norm(a - vo.ref_reconstruct_vis(u, s, vt))
+    assert abs(np.linalg.norm(a - theirs) - e_ref) <= 1e-5 * e_ref + 5e-6 * np.linalg.norm(a)

@@ -58,3 +58,109 @@ def apply_svd_batched(cube, decorrelation: float = None, compressionrank: int = 
         return []
     U, S, Vt, ranks, _ = get_engine().compress_host(cube, decorrelation, compressionrank)
     return [(U[b, :, :k].copy(), S[b, :k].copy(), Vt[b, :k, :].copy()) for b, k in enumerate(ranks.tolist())]
+
+
+# =====================================================================================================================
+# Callers on the compression side of the hot path: baseline discovery, batching,
+# per-(baseline, correlation) gather, leaf tree. Mirrors reference compress_ms.py:366-703 with the per-matrix dask
+# tasks replaced by ONE apply_svd_batched call per batch of baselines.
+# =====================================================================================================================
+def batch_baselines(baselines, batch_size):
+    """Split the baseline list into batches of `batch_size` (reference compress_ms.py:366-386)."""
+    batch_size = max(1, int(batch_size))
+    return [baselines[i:i + batch_size] for i in range(0, len(baselines), batch_size)]
+
+
+def _leaf_jobs(vis, baseline_batch, correlation, correlation_optimized):
+    """Yield (leaf name parts, matrix, rowid) for every SVD of a batch (reference compress_ms.py:588-688)."""
+    corr_names = [c.strip() for c in correlation.split(",") if c.strip()]
+    for a1, a2 in baseline_batch:
+        rows = vis.baseline_rows(int(a1), int(a2))
+        if rows.size == 0:
+            continue
+        rowid = vis.rowid[rows]
+        name = f"{vis.antenna_names[int(a1)]}&{vis.antenna_names[int(a2)]}"
+        block = vis.data[rows]                                  # [time, chan, corr] of this baseline
+        if correlation_optimized:
+            # XX and YY stacked -> "diagonals", XY and YX stacked -> "offdiagonals" (reference :600-657; the reference
+            # hard-codes the casacore enums 9/12 and 10/11 here)
+            if "XX" in corr_names and "YY" in corr_names:
+                m = np.vstack([block[:, :, vis.corr_index(9)], block[:, :, vis.corr_index(12)]])
+                yield (name, "diagonals"), m, np.tile(rowid, 2)
+            if "XY" in corr_names and "YX" in corr_names:
+                m = np.vstack([block[:, :, vis.corr_index(10)], block[:, :, vis.corr_index(11)]])
+                yield (name, "offdiagonals"), m, np.tile(rowid, 2)
+        else:
+            for c in corr_names:
+                yield (name, c), block[:, :, vis.corr_index(c)], rowid
+
+
+def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_optimized=False, decorrelation=None,
+                     compressionrank=None, outcolumn="COMPRESSED_DATA", compressor="zstd", level=4, batch_size=20,
+                     antennas=None):
+    """Compress every (baseline, correlation) matrix of `vis` (a visco_b200.msdata.VisData) and write the leaf tree
+    ``<zarr>/MAIN/<outcolumn>/<ANT1>&<ANT2>/<corr>/`` (reference compress_visdata, compress_ms.py:389-703).
+    Returns the number of baselines processed."""
+    from pathlib import Path
+
+    from .zarr_leaf import write_svd_to_zarr
+    baselines = vis.baselines(antennas)
+    processed = 0
+    for batch in batch_baselines(baselines, batch_size):
+        jobs = list(_leaf_jobs(vis, batch, correlation, correlation_optimized))
+        # one GPU call per distinct matrix shape of the batch (baselines can have different numbers of rows)
+        by_shape = {}
+        for j, (_, m, _) in enumerate(jobs):
+            by_shape.setdefault(m.shape, []).append(j)
+        results = [None] * len(jobs)
+        for shape, idx in by_shape.items():
+            cube = np.stack([jobs[j][1] for j in idx]).astype(np.complex64, copy=False)
+            for j, res in zip(idx, apply_svd_batched(cube, decorrelation, compressionrank)):
+                results[j] = res
+        for (parts, _, rowid), res in zip(jobs, results):
+            leaf = Path(zarr_output_path) / "MAIN" / f"{outcolumn}" / parts[0] / parts[1]
+            write_svd_to_zarr(res, leaf, compressor, level, rowid)
+        processed += len(batch)
+    return processed
+
+
+def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, chunk_size_row: int = 10000,
+                     overwrite: bool = True, compressor: str = "zstd", level: int = 4, nworkers: int = 4,
+                     nthreads: int = 2, memory_limit: str = "4GB", direct_to_workers: bool = True,
+                     correlation: str = "XX,YY", correlation_optimized: bool = False, fieldid: int = 0, ddid: int = 0,
+                     scan: int = 1, column: str = "DATA", outcolumn: str = "COMPRESSED_DATA", batch_size: int = 20,
+                     dashboard_addr: str = None, host_addr: str = None, use_model_data: bool = False,
+                     model_data: str = None, flag_estimate: bool = False, decorrelation: float = None,
+                     compressionrank: int = None, flagvalue: int = None, antennas: list = None):
+    """Same keyword arguments as the reference's compress_full_ms (compress_ms.py:782-811). The dask-cluster arguments
+    (nworkers, nthreads, memory_limit, direct_to_workers, dashboard_addr, host_addr, chunk_size_row) are accepted and
+    ignored: the batches run on the GPU of this process. Flag-value replacement (use_model_data / flag_estimate /
+    flagvalue, compress_ms.py:530-566) is outside the hot path and not implemented: passing them raises."""
+    import os
+    import shutil
+
+    from .msdata import VisData
+    from .zarr_leaf import write_group
+    if not os.path.exists(ms_path):
+        raise ValueError(f"MS path {ms_path} does not exist.")                     # reference :876-877
+    if use_model_data or flag_estimate or flagvalue is not None:
+        raise NotImplementedError("flag replacement (use_model_data / flag_estimate / flagvalue) is out of scope")
+    if compressor is not None:
+        from .zarr_leaf import get_compressor
+        get_compressor(compressor, level)                                          # ValueError for unknown names (:51)
+    vis = VisData.load(ms_path, column=column, scan=scan, fieldid=fieldid, ddid=ddid)
+    if overwrite and os.path.exists(zarr_path):
+        shutil.rmtree(zarr_path)                                                   # reference :95-96
+    os.makedirs(zarr_path, exist_ok=True)
+    # the few MAIN / ANTENNA / POLARIZATION columns the decompressor needs (the full MS -> zarr conversion is out of scope)
+    nrow, nchan, ncorr = vis.data.shape
+    write_group(os.path.join(zarr_path, "MAIN"),
+                {"ANTENNA1": (vis.antenna1, ("row",)), "ANTENNA2": (vis.antenna2, ("row",)), "ROWID": (vis.rowid, ("row",))},
+                attrs={"visco_b200": {"data_shape": [nrow, nchan, ncorr], "data_dtype": "<c8", "column": column,
+                                      "outcolumn": outcolumn}})
+    write_group(os.path.join(zarr_path, "ANTENNA"), {"NAME": (np.array(vis.antenna_names, dtype="U"), ("row",))})
+    write_group(os.path.join(zarr_path, "POLARIZATION"),
+                {"CORR_TYPE": (np.array([vis.corr_types], dtype=np.int32), ("row", "corr"))})
+    return compress_visdata(vis, zarr_path, correlation=correlation, correlation_optimized=correlation_optimized,
+                            decorrelation=decorrelation, compressionrank=compressionrank, outcolumn=outcolumn,
+                            compressor=compressor, level=level, batch_size=batch_size, antennas=antennas)
