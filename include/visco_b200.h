@@ -111,6 +111,18 @@ int vk_uses_small_path(int m, int n);
 /* 1 if the tcgen05 Gram kernel handles (m, n, side), else 0 (SIMT Gram). */
 int vk_gram_uses_tcgen05(int m, int n, int side);
 
+/* ---- layout on either side of the path ---------------------------------------------------- */
+/* Gather per-(baseline, correlation) matrices out of an MS column data[row][chan][corr] (complex64, corr fastest):
+ *   stack == 1:  A[bl * ncs + j][t][v]                    = data[row_idx[bl][t]][v][corr_sel[bl][j]]
+ *   stack == 2:  A[bl * (ncs/2) + j/2][(j%2) * m + t][v]  = ...   (--correlation-optimized vstack of two correlations)
+ * row_idx is [nbl][m], corr_sel is [nbl][ncs] (correlation planes per baseline entry).
+ * Replaces the boolean-mask isel and [:, :, ci] slicing of compress_ms.py:591-592,604-608,664. row_idx < 0 = padding.
+ * vk_scatter_baselines is the inverse (decompress_ms.py:216-232 incl. unstack_vis :95-104). */
+int vk_gather_baselines(vk_handle h, const void* data_dev, int nchan, int ncorr, const int32_t* row_idx_dev, int nbl,
+                        int m, const int32_t* corr_sel_dev, int ncs, int stack, void* A_dev);
+int vk_scatter_baselines(vk_handle h, const void* cube_dev, int nchan, int ncorr, const int32_t* row_idx_dev, int nbl,
+                         int m, const int32_t* corr_sel_dev, int ncs, int stack, void* data_dev);
+
 /* ---- benchmark generator (SURVEY.md section 8d model), on device ------------------------------------------ */
 /* A[b] for b = baseline * ncorr + corr; global baseline index = bl_offset + baseline out of nbl_total. */
 int vk_synth_fill(vk_handle h, void* A_dev, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,

@@ -30,6 +30,8 @@ SIGNATURES = {
     "vk_svd_jacobi_small_batched": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "vk_uses_small_path": (_i, [_i, _i]),
     "vk_gram_uses_tcgen05": (_i, [_i, _i, _i]),
+    "vk_gather_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "vk_scatter_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "vk_synth_fill": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _u64]),
     "vk_launch_count": (C.c_int64, [_vp]),
     "vk_last_stage_ms": (_i, [_vp, C.POINTER(_f)]),

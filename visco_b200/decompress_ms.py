@@ -97,18 +97,25 @@ def _store_index(zarr_path):
 
 def construct_main_ds(zarr_path: str, column: str, batch_size: int):
     """Rebuild the visibility column from the leaf tree (reference construct_main_ds, decompress_ms.py:134-234).
+
+    Device pipeline: per batch the zero-padded factors go to the GPU, vk_reconstruct_batched forms the matrices and
+    vk_scatter_baselines writes them straight into the (row, chan, corr) column held on the device (including the
+    unstacking of "diagonals" / "offdiagonals" leaves); the column comes back to the host once at the end.
     Returns a visco_b200.msdata.VisData whose `data` is the reconstructed [row, chan, corr] complex64 array."""
     import os
+
+    import torch
 
     from . import LOG
     from .msdata import VisData
     from .zarr_leaf import list_subtables, read_svd_from_zarr
+    eng = get_engine()
+    dev = f"cuda:{eng.device}"
     ant1, ant2, rowid, antnames, shape = _store_index(zarr_path)
     base = os.path.join(zarr_path, "MAIN", column)
-    baselines = list_subtables(base)
-    tasks = []                                         # (U, S, WT, row_indices, corr_name)
+    tasks = []                                         # (U, S, WT, row_indices, corr planes, stack)
     nchan = None
-    for baseline in baselines:
+    for baseline in list_subtables(base):
         correlations = list_subtables(os.path.join(base, baseline))
         if "&" not in baseline or not correlations:
             continue
@@ -116,8 +123,7 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         if a1n not in antnames or a2n not in antnames:
             LOG.warning(f"Baseline {baseline} not found in ANTENNA table. Skipping.")      # reference :175-177
             continue
-        a1, a2 = antnames.index(a1n), antnames.index(a2n)
-        row_indices = np.nonzero((ant1 == a1) & (ant2 == a2))[0]
+        row_indices = np.nonzero((ant1 == antnames.index(a1n)) & (ant2 == antnames.index(a2n)))[0]
         for corr_name in correlations:
             U, S, WT, _ = read_svd_from_zarr(os.path.join(base, baseline, corr_name))
             nchan = WT.shape[1]
@@ -126,30 +132,36 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         if nchan is None:
             raise ValueError(f"{zarr_path} holds no factor leaves under MAIN/{column}")
         shape = [len(ant1), nchan, 4]
-    out = np.zeros(tuple(shape), dtype=np.complex64)
-    corr_indices = {"XX": 0, "XY": 1, "YX": 2, "YY": -1}                                  # reference :182
+    ncorr = int(shape[2])
+    planes = {"XX": (0,), "XY": (1,), "YX": (2,), "YY": (ncorr - 1,),                     # reference :182 (YY = -1)
+              "diagonals": (0, 3), "offdiagonals": (1, 2)}                                 # reference :222-229
+    out_dev = torch.zeros(tuple(int(x) for x in shape), dtype=torch.complex64, device=dev)
     batch_size = max(1, int(batch_size))
     for start in range(0, len(tasks), batch_size):
         batch = tasks[start:start + batch_size]
-        by_shape = {}
-        for j, t in enumerate(batch):
-            by_shape.setdefault((t[0].shape[0], t[2].shape[1]), []).append(j)
-        for _, idx in by_shape.items():
-            rec = reconstruct_vis_batched([batch[j][:3] for j in idx])
-            for j, vis in zip(idx, rec):
-                _, _, _, row_indices, corr_name = batch[j]
-                nrows = row_indices.size
-                if corr_name == "diagonals":                                             # reference :222-225
-                    parts = unstack_vis(vis, nrows)
-                    out[row_indices, :, 0] = parts[0]
-                    out[row_indices, :, 3] = parts[1]
-                elif corr_name == "offdiagonals":                                        # reference :226-229
-                    parts = unstack_vis(vis, nrows)
-                    out[row_indices, :, 1] = parts[0]
-                    out[row_indices, :, 2] = parts[1]
-                else:
-                    out[row_indices, :, corr_indices[corr_name]] = vis
-    corr_types = [9, 10, 11, 12][: out.shape[2]] if out.shape[2] <= 4 else list(range(out.shape[2]))
+        groups = {}
+        for t in batch:
+            if t[4] not in planes:
+                raise ValueError(f"unknown leaf name {t[4]}")
+            stack = len(planes[t[4]])
+            if t[0].shape[0] != stack * t[3].size:
+                raise ValueError(f"leaf {t[4]} has {t[0].shape[0]} rows, the table has {t[3].size} for this baseline")
+            groups.setdefault((t[3].size, t[2].shape[1], stack), []).append(t)
+        for (m, n, stack), ts in groups.items():
+            B = len(ts)
+            kmax = max(1, max(t[1].shape[0] for t in ts))
+            U = np.zeros((B, stack * m, kmax), np.complex64)
+            S = np.zeros((B, kmax), np.float32)
+            Vt = np.zeros((B, kmax, n), np.complex64)
+            for b, t in enumerate(ts):
+                k = t[1].shape[0]
+                U[b, :, :k], S[b, :k], Vt[b, :k, :] = t[0], t[1], t[2]
+            rec = eng.reconstruct(torch.from_numpy(U).to(dev), torch.from_numpy(S).to(dev), torch.from_numpy(Vt).to(dev))
+            row_idx = torch.from_numpy(np.stack([t[3] for t in ts]).astype(np.int32)).to(dev)
+            corr_sel = torch.tensor([list(planes[t[4]]) for t in ts], dtype=torch.int32, device=dev)
+            eng.scatter_baselines(rec, out_dev, row_idx, corr_sel, stack)
+    out = out_dev.cpu().numpy()
+    corr_types = [9, 10, 11, 12][:ncorr] if ncorr <= 4 else list(range(ncorr))
     return VisData(data=out, antenna1=ant1, antenna2=ant2, antenna_names=antnames, corr_types=corr_types, rowid=rowid)
 
 

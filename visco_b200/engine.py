@@ -149,6 +149,41 @@ class Engine:
         self._check(rc, "vk_synth_fill")
         return A
 
+    # layout kernels on either side of the path
+    def gather_baselines(self, data, row_idx, corr_sel, stack=1, out=None):
+        """data: CUDA complex64 [row, chan, corr]; row_idx: CUDA int32 [nbl, m] (-1 = padding); corr_sel: CUDA int32
+        [nbl, ncs] correlation planes per entry. Returns the cube [nbl * ncs / stack, stack * m, chan] (reference compress_ms.py:591-664)."""
+        torch = _torch()
+        nrow, nchan, ncorr = data.shape
+        nbl, m = row_idx.shape
+        ncs = corr_sel.shape[1]
+        assert data.is_contiguous() and row_idx.dtype == torch.int32 and corr_sel.dtype == torch.int32
+        assert corr_sel.shape[0] == nbl and row_idx.is_contiguous() and corr_sel.is_contiguous()
+        if out is None:
+            out = torch.zeros((nbl * ncs // stack, stack * m, nchan), dtype=torch.complex64, device=data.device)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_gather_baselines(self.h, self._ptr(data), nchan, ncorr, self._ptr(row_idx), nbl, m,
+                                              self._ptr(corr_sel), ncs, stack, self._ptr(out))
+        self._check(rc, "vk_gather_baselines")
+        return out
+
+    def scatter_baselines(self, cube, data, row_idx, corr_sel, stack=1):
+        """Inverse of gather_baselines: writes the matrices of `cube` into data[row, chan, corr] in place
+        (reference decompress_ms.py:216-232)."""
+        torch = _torch()
+        nrow, nchan, ncorr = data.shape
+        nbl, m = row_idx.shape
+        ncs = corr_sel.shape[1]
+        assert corr_sel.shape[0] == nbl and row_idx.is_contiguous() and corr_sel.is_contiguous()
+        assert cube.is_contiguous() and data.is_contiguous() and cube.shape == (nbl * ncs // stack, stack * m, nchan)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_scatter_baselines(self.h, self._ptr(cube), nchan, ncorr, self._ptr(row_idx), nbl, m,
+                                               self._ptr(corr_sel), ncs, stack, self._ptr(data))
+        self._check(rc, "vk_scatter_baselines")
+        return data
+
     # stage-level (tests / profiling)
     def gram(self, A, impl=0):
         torch = _torch()
