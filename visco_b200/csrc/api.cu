@@ -9,7 +9,7 @@ namespace {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, total;
+    size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, xbuf, total;
 };
 
 bool small_path(int m, int n) {
@@ -37,6 +37,9 @@ WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0) {
     w.active = off, off += 256;
     w.nonfinite = off, off += 256;
     w.norm2 = off, off += align_up((size_t)chunk * kmax * 4);
+    // K-major copy of conj(U_k)^T for the tcgen05 V-formation (wide Gram path, k > 8)
+    w.xbuf = off;
+    if (!small_path(m, n) && m <= n && vk_cgemm_tc_supported(m, n, kmax)) off += align_up((size_t)chunk * kmax * m * 8);
     w.total = off;
     return w;
 }
@@ -159,7 +162,8 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
                                    ranks, stats, sweeps, done)))
             return rc;
         tm.mark(3);
-        if ((rc = vk_launch_factors_gram(h, A, W, B, m, n, side, kmax, perm, inv, ranks, norm2, U, S, Vt, stats)))
+        float2* xbuf = (side == 0 && vk_cgemm_tc_supported(m, n, kmax)) ? reinterpret_cast<float2*>(ws + L.xbuf) : nullptr;
+        if ((rc = vk_launch_factors_gram(h, A, W, B, m, n, side, kmax, perm, inv, ranks, norm2, U, S, Vt, stats, xbuf)))
             return rc;
         tm.mark(4);
         tm.collect(0, 0, 1);
@@ -272,6 +276,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_bsz = (int)v;
     else if (k == "stage_timing")
         h->stage_timing = (int)v;
+    else if (k == "gemm_impl")
+        h->gemm_impl = (int)v;
     else if (k == "recon_generic")
         h->recon_generic = (int)v;
     else if (k == "jacobi_generic")

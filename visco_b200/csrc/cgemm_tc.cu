@@ -1,0 +1,472 @@
+// Batched complex GEMM on tcgen05 for the two large-rank products of the path (north_star items (c) and (d) at k > 8):
+//
+//   MODE_FORMV:  Vt[c][v]  = sum_t  X[c][t] * A[t][v]        X = conj(U_k)^T / lambda (materialised, [B][kmax][m])
+//   MODE_RECON:  out[t][v] = sum_c  U[t][c] * (S[c] Vt[c][v])
+//
+// i.e. D[M x N] = P[M x K] * Q[K x N] with P K-major (its contraction index is contiguous in memory) and Q N-major
+// (its output index is contiguous). Replaces the BLAS cgemm behind `U_mult_S @ Vt` (reference decompress_ms.py:131)
+// and the right-vector part of LAPACK cgesdd (reference compress_ms.py:350).
+//
+// Complex arithmetic on a real tensor core: the A operand is the real view of P (row i = [pr(i,0), pi(i,0), pr(i,1), ...],
+// 2K floats, K-major). The B operand is a 2K x 2N real matrix built on the fly in shared memory from the rows of Q:
+// contraction row 2k = the raw row (qr, qi interleaved along N), row 2k+1 = (-qi, qr), so that D's real view comes out
+// directly as interleaved complex64:  D[i][2v] = sum pr*qr - pi*qi ,  D[i][2v+1] = sum pr*qi + pi*qr.
+// Both operands are split hi + lo (TF32, round-to-nearest) and multiplied as hi*hi + hi*lo + lo*hi (3xTF32); MMA chains are
+// CHUNK_KB K-blocks long into ping-pong TMEM accumulators that the converter warps promote into fp32 registers with
+// round-to-nearest adds (see gram_tc.cu for why).
+//
+// One CTA computes a 128 x 128 complex tile. Warp roles: warp 0 TMA producer (A operand: 3-D map, SWIZZLE_128B boxes of
+// 128 rows x 32 floats; B operand: 4-D map over (32 floats, contraction row, 32-float group, batch) so that the box
+// {32, 16, 8, 1} lands as 8 groups of 16 rows x 128 bytes), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11
+// converters (A: split in place; B: un-swizzle the raw row, optionally scale it by S[c], write rows 2k / 2k+1 of the
+// MN-major SWIZZLE_128B_BASE32B operand, hi and lo) and promoters / epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int TILE_NC = 128;              // complex output columns per tile = 256 floats = MMA N
+constexpr int KB_C = 16;                  // complex contraction elements per K-block (32 floats of A, 32 rows of B)
+constexpr int NSTAGE = 2;
+constexpr uint32_t A_BYTES = TILE_M * 128;        // 16 KiB  (128 rows x 32 floats)
+constexpr uint32_t BRAW_BYTES = 8 * KB_C * 128;   // 16 KiB  (8 groups x 16 rows x 128 B)
+constexpr uint32_t BCONV_BYTES = 8 * 2 * KB_C * 128;  // 32 KiB (8 groups x 32 rows x 128 B)
+constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_RAW = 2 * A_BYTES, OFF_B_HI = 2 * A_BYTES + BRAW_BYTES,
+                   OFF_B_LO = 2 * A_BYTES + BRAW_BYTES + BCONV_BYTES;
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + BRAW_BYTES + 2 * BCONV_BYTES;  // 112 KiB
+constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + 128 + 1024;
+constexpr int NUM_CONVERTERS = 256;
+constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int CHUNK_KB = 4;
+
+enum { MODE_FORMV = 0, MODE_RECON = 1 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// MN-major operand. For 32-bit (tf32) MN-major data the only layout the tensor core accepts is SWIZZLE_128B_BASE32B
+// (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type 1): 32 MN elements (128 bytes) contiguous per contraction row, atoms
+// of FOUR contraction rows (512 bytes), and inside an atom the 32-byte chunk index is XOR-ed with the row index
+// (Swizzle<2,5,2> on byte addresses). Leading byte offset = distance between 32-element MN groups, stride byte offset =
+// distance between 4-row contraction groups (make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+struct Split4 {
+    float4 hi, lo;
+};
+__device__ __forceinline__ Split4 split4(float4 v) {
+    Split4 s;
+    s.hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    s.lo = make_float4(to_tf32(v.x - s.hi.x), to_tf32(v.y - s.hi.y), to_tf32(v.z - s.hi.z), to_tf32(v.w - s.hi.w));
+    return s;
+}
+// (r0, i0, r1, i1) -> (-i0, r0, -i1, r1) : the row that multiplies the imaginary part of the A operand
+__device__ __forceinline__ float4 rot90(float4 v) { return make_float4(-v.y, v.x, -v.w, v.z); }
+
+// promote one finished chunk: this thread's row x 128 consecutive accumulator columns (64 complex outputs)
+__device__ __forceinline__ void drain_chunk(int c, uint32_t bar_accf, uint32_t bar_acce, uint32_t tmem_base, int quad,
+                                            int chalf, float (&acc)[128]) {
+    const int p = c & 1;
+    mbar_wait(bar_accf + 8 * p, ((uint32_t)c >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(p * 256 + chalf * 128);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint32_t a[16], b[16];
+        tmem_ld16(taddr + g * 32, a);
+        tmem_ld16(taddr + g * 32 + 16, b);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            acc[g * 32 + j] += __uint_as_float(a[j]);
+            acc[g * 32 + 16 + j] += __uint_as_float(b[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(bar_acce + 8 * p);
+}
+
+struct GemmArgs {
+    float2* D;             // output [B][Mtot][ldn] complex
+    const int32_t* ranks;  // [B]
+    const float* S;        // MODE_RECON: [B][kmax] scale of contraction row c
+    float* norm2;          // MODE_FORMV: [B][kmax] accumulates sum_v |D[c][v]|^2
+    int Mtot;              // rows of D that must be written (kmax for FORMV, m for RECON)
+    int Ntot;              // complex columns (n)
+    int Ktot;              // complex contraction length available (m for FORMV, kmax for RECON)
+    int kmax;
+    int tiles_m, tiles_n;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + OFF_BARS;
+    const uint32_t bar_raw = bars, bar_conv = bars + 16, bar_empty = bars + 32, bar_accf = bars + 48, bar_acce = bars + 64;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 96);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = g.tiles_m * g.tiles_n;
+    const int b = blockIdx.x / tiles;
+    const int tile = blockIdx.x - b * tiles;
+    const int m0 = (tile / g.tiles_n) * TILE_M;
+    const int n0c = (tile % g.tiles_n) * TILE_NC;  // first complex column
+    const int rank = min(g.ranks ? g.ranks[b] : g.kmax, g.kmax);
+    // valid extents for this matrix
+    const int Mvalid = MODE == MODE_FORMV ? rank : g.Mtot;
+    const int Kvalid = MODE == MODE_FORMV ? g.Ktot : rank;
+    const int KB = (m0 < Mvalid) ? (Kvalid + KB_C - 1) / KB_C : 0;  // nothing to multiply for all-padding tiles
+    const int NC = (KB + CHUNK_KB - 1) / CHUNK_KB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_raw + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, NUM_CONVERTERS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int p = 0; p < 2; ++p) {
+            mbar_init(bar_accf + 8 * p, 1);
+            mbar_init(bar_acce + 8 * p, NUM_CONVERTERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+      if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
+                mbar_wait(bar_empty + 8 * s, (use & 1) ^ 1);
+                const uint32_t st = sbase + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_raw + 8 * s, A_BYTES + BRAW_BYTES);
+                tma_load_3d(st + OFF_A_HI, &mapA, bar_raw + 8 * s, kb * 2 * KB_C, m0, b);
+                tma_load_4d(st + OFF_B_RAW, &mapB, bar_raw + 8 * s, 0, kb * KB_C, n0c * 2 / 32, b);
+            }
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // D = f32, A = B = tf32, A K-major, B MN-major (bit 16), N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
+                const int c = kb / CHUNK_KB, p = c & 1;
+                const bool first = (kb % CHUNK_KB) == 0;
+                if (first) {
+                    mbar_wait(bar_acce + 8 * p, (((uint32_t)c >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(bar_conv + 8 * s, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = sbase + s * STAGE_BYTES;
+                const uint64_t a_hi = desc_kmajor(st + OFF_A_HI), a_lo = desc_kmajor(st + OFF_A_LO);
+                const uint32_t d = tmem_base + (uint32_t)p * 256u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {  // 4 MMAs of K = 8 floats per K-block of 32
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    // B: contraction rows 8k .. 8k+7 of every 32-float group: atom k of each group
+                    const uint64_t b_hi = desc_mnmajor(st + OFF_B_HI + k * 1024, 2 * KB_C * 128, 512);
+                    const uint64_t b_lo = desc_mnmajor(st + OFF_B_LO + k * 1024, 2 * KB_C * 128, 512);
+                    umma_tf32(d, a_lo + adv, b_hi, idesc, !(first && k == 0));
+                    umma_tf32(d, a_hi + adv, b_lo, idesc, 1);
+                    umma_tf32(d, a_hi + adv, b_hi, idesc, 1);
+                }
+                umma_commit(bar_empty + 8 * s);
+                if ((kb % CHUNK_KB) == CHUNK_KB - 1 || kb == KB - 1) umma_commit(bar_accf + 8 * p);
+            }
+        }
+      }
+    } else {
+        // ===================== converters / promoters / epilogue =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int ct = threadIdx.x - 128;
+        const int quad = warp & 3;
+        const int chalf = (warp - 4) >> 2;  // which 128-float half of the 256 accumulator columns
+        float acc[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+        int next_drain = 0;
+
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % NSTAGE;
+            const uint32_t use = kb / NSTAGE;
+            mbar_wait(bar_raw + 8 * s, use & 1);
+            unsigned char* st = smem + s * STAGE_BYTES;
+            float4* a_hi = reinterpret_cast<float4*>(st + OFF_A_HI);
+            float4* a_lo = reinterpret_cast<float4*>(st + OFF_A_LO);
+            const float4* b_raw = reinterpret_cast<const float4*>(st + OFF_B_RAW);
+            unsigned char* b_hi = st + OFF_B_HI;
+            unsigned char* b_lo = st + OFF_B_LO;
+#pragma unroll 2
+            for (int i = 0; i < (int)(A_BYTES / 16) / NUM_CONVERTERS; ++i) {
+                const int c = ct + i * NUM_CONVERTERS;
+                const Split4 sa = split4(a_hi[c]);
+                a_hi[c] = sa.hi;
+                a_lo[c] = sa.lo;
+            }
+#pragma unroll 2
+            for (int i = 0; i < (int)(BRAW_BYTES / 16) / NUM_CONVERTERS; ++i) {
+                const int c = ct + i * NUM_CONVERTERS;      // physical 16-byte chunk of the raw tile
+                const int grp = c >> 7;                      // 32-float group (16 rows x 8 chunks = 128 chunks each)
+                const int t = (c >> 3) & (KB_C - 1);         // contraction row inside the K-block
+                const int lc = (c & 7) ^ (t & 7);            // logical chunk: TMA swizzled it with the row index
+                float4 v = b_raw[c];
+                if (MODE == MODE_RECON) {
+                    const int cc = kb * KB_C + t;
+                    const float sc = cc < g.kmax ? g.S[(size_t)b * g.kmax + cc] : 0.f;
+                    v.x *= sc;
+                    v.y *= sc;
+                    v.z *= sc;
+                    v.w *= sc;
+                }
+                const Split4 s0 = split4(v);
+                const Split4 s1 = split4(rot90(v));
+                const int r0 = 2 * t, r1 = 2 * t + 1;        // rows of the 2K x 2N real operand
+                // destination swizzle (BASE32B): 32-byte chunk index (lc >> 1) XOR (row & 3); 16-byte halves keep their order
+                const uint32_t o0 = (uint32_t)(grp * 2 * KB_C + r0) * 128 + (uint32_t)(((((lc >> 1) ^ (r0 & 3)) << 1) | (lc & 1)) << 4);
+                const uint32_t o1 = (uint32_t)(grp * 2 * KB_C + r1) * 128 + (uint32_t)(((((lc >> 1) ^ (r1 & 3)) << 1) | (lc & 1)) << 4);
+                *reinterpret_cast<float4*>(b_hi + o0) = s0.hi;
+                *reinterpret_cast<float4*>(b_lo + o0) = s0.lo;
+                *reinterpret_cast<float4*>(b_hi + o1) = s1.hi;
+                *reinterpret_cast<float4*>(b_lo + o1) = s1.lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_conv + 8 * s);
+            if (kb >= CHUNK_KB + 1 && ((kb - 1) % CHUNK_KB) == 0)
+                drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
+        }
+        while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
+
+        // ---- epilogue: this thread holds row (m0 + quad*32 + lane), complex columns n0c + chalf*64 .. +63 ----
+        const int gi = m0 + quad * 32 + lane;
+        if (gi < g.Mtot) {
+            const bool valid_row = gi < Mvalid;
+            float2* drow = g.D + ((size_t)b * g.Mtot + gi) * g.Ntot;
+            float nsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+                const int v = n0c + chalf * 64 + j;
+                float4 o = valid_row ? make_float4(acc[2 * j], acc[2 * j + 1], acc[2 * j + 2], acc[2 * j + 3])
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v + 1 < g.Ntot) {
+                    *reinterpret_cast<float4*>(drow + v) = o;
+                    nsum += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+                } else if (v < g.Ntot) {
+                    drow[v] = make_float2(o.x, o.y);
+                    nsum += o.x * o.x + o.y * o.y;
+                }
+            }
+            if (MODE == MODE_FORMV && valid_row) atomicAdd(&g.norm2[(size_t)b * g.kmax + gi], nsum);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// A operand: P[b][rows][kc] complex, K-major: real view dims (2*kc, rows, B)
+int make_map_a(vk_context* h, CUtensorMap* map, const float2* P, int rows, int kc, int nb) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * kc, (cuuint64_t)rows, (cuuint64_t)nb};
+    const cuuint64_t strides[2] = {(cuuint64_t)2 * kc * 4, (cuuint64_t)rows * 2 * kc * 4};
+    const cuuint32_t box[3] = {32, TILE_M, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(P), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (A operand) failed: " + std::to_string((int)r));
+    return VK_OK;
+}
+// B operand: Q[b][krows][nc] complex, N contiguous: view (32 floats, krows, 2*nc/32 groups, B); box {32, 16, 8, 1}
+int make_map_b(vk_context* h, CUtensorMap* map, const float2* Q, int krows, int nc, int nb) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    const cuuint64_t dims[4] = {32, (cuuint64_t)krows, (cuuint64_t)(2 * nc / 32), (cuuint64_t)nb};
+    const cuuint64_t strides[3] = {(cuuint64_t)2 * nc * 4, 128, (cuuint64_t)krows * 2 * nc * 4};
+    const cuuint32_t box[4] = {32, KB_C, 8, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(Q), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (B operand) failed: " + std::to_string((int)r));
+    return VK_OK;
+}
+
+}  // namespace
+
+bool vk_cgemm_tc_supported(int m, int n, int kmax) {
+    // tensor maps need 16-byte strides (kmax even) and whole 32-float groups along the channel axis (n % 16 == 0)
+    return kmax > 8 && (kmax % 2) == 0 && (n % 16) == 0 && m >= 1;
+}
+
+// Vt[b][c][:] = sum_t X[b][c][t] A[b][t][:]   (rows c >= ranks[b] are written as zeros); norm2[b][c] += |Vt[b][c]|^2
+int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const int32_t* ranks, float2* Vt, float* norm2,
+                       int B, int m, int n, int kmax) {
+    VK_CUDA(h, cudaFuncSetAttribute(cgemm_tc_kernel<MODE_FORMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int maxB = 16384;
+    for (int b0 = 0; b0 < B; b0 += maxB) {
+        const int nb = (B - b0) < maxB ? (B - b0) : maxB;
+        CUtensorMap ma, mb;
+        int rc;
+        if ((rc = make_map_a(h, &ma, X + (size_t)b0 * kmax * m, kmax, m, nb))) return rc;
+        if ((rc = make_map_b(h, &mb, A + (size_t)b0 * m * n, m, n, nb))) return rc;
+        GemmArgs g;
+        g.D = Vt + (size_t)b0 * kmax * n;
+        g.ranks = ranks + b0;
+        g.S = nullptr;
+        g.norm2 = norm2 + (size_t)b0 * kmax;
+        g.Mtot = kmax;
+        g.Ntot = n;
+        g.Ktot = m;
+        g.kmax = kmax;
+        g.tiles_m = (kmax + TILE_M - 1) / TILE_M;
+        g.tiles_n = (n + TILE_NC - 1) / TILE_NC;
+        cgemm_tc_kernel<MODE_FORMV><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}
+
+// out[b][t][:] = sum_{c < ranks[b]} U[b][t][c] S[b][c] Vt[b][c][:]
+int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, float2* out,
+                       int B, int m, int n, int kmax) {
+    VK_CUDA(h, cudaFuncSetAttribute(cgemm_tc_kernel<MODE_RECON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int maxB = 16384;
+    for (int b0 = 0; b0 < B; b0 += maxB) {
+        const int nb = (B - b0) < maxB ? (B - b0) : maxB;
+        CUtensorMap ma, mb;
+        int rc;
+        if ((rc = make_map_a(h, &ma, U + (size_t)b0 * m * kmax, m, kmax, nb))) return rc;
+        if ((rc = make_map_b(h, &mb, Vt + (size_t)b0 * kmax * n, kmax, n, nb))) return rc;
+        GemmArgs g;
+        g.D = out + (size_t)b0 * m * n;
+        g.ranks = ranks ? ranks + b0 : nullptr;
+        g.S = S + (size_t)b0 * kmax;
+        g.norm2 = nullptr;
+        g.Mtot = m;
+        g.Ntot = n;
+        g.Ktot = kmax;
+        g.kmax = kmax;
+        g.tiles_m = (m + TILE_M - 1) / TILE_M;
+        g.tiles_n = (n + TILE_NC - 1) / TILE_NC;
+        cgemm_tc_kernel<MODE_RECON><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}

@@ -34,6 +34,7 @@ struct vk_context {
     cudaEvent_t fork_ev = nullptr;
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
+    int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -122,10 +123,15 @@ int vk_launch_find_n(vk_context* h, const float* S, int B, int r, double decorre
 // factor formation
 int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int B, int m, int n, int side, int kmax,
                            const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float* norm2_dev,
-                           float2* U, float* S, float2* Vt, float* stats_dev);
+                           float2* U, float* S, float2* Vt, float* stats_dev, float2* xbuf);
 int vk_launch_factors_small(vk_context* h, const float2* W, int ld, int B, int m, int n, int kmax,
                             const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float2* U,
                             float2* Vt);
+bool vk_cgemm_tc_supported(int m, int n, int kmax);
+int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const int32_t* ranks, float2* Vt, float* norm2,
+                       int B, int m, int n, int kmax);
+int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, float2* out,
+                       int B, int m, int n, int kmax);
 int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
                           int m, int n, int kmax, float2* out);
 int vk_launch_synth(vk_context* h, float2* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,

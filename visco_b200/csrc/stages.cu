@@ -769,7 +769,7 @@ int vk_launch_factors_small(vk_context* h, const float2* W, int ld, int B, int m
 
 int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int B, int m, int n, int side, int kmax,
                            const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float* norm2_dev,
-                           float2* U, float* S, float2* Vt, float* stats_dev) {
+                           float2* U, float* S, float2* Vt, float* stats_dev, float2* xbuf) {
     int rc;
     VK_CUDA(h, cudaMemsetAsync(norm2_dev, 0, sizeof(float) * (size_t)B * kmax, h->stream));
     if (side == 0) {
@@ -777,7 +777,11 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
         if ((rc = launch_cols(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
         FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
         const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16 == 0);
-        if (aligned && kmax <= 8 && (size_t)m * 8 * sizeof(float4) <= VK_SMEM_BUDGET && !h->recon_generic) {
+        if (xbuf && h->gemm_impl == 0 && vk_cgemm_tc_supported(m, n, kmax)) {
+            // large rank: X = conj(U_k)^T / lambda materialised K-major, then the tcgen05 complex GEMM
+            if ((rc = launch_rows(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 1, 1, xbuf, B))) return rc;
+            rc = vk_launch_formv_tc(h, xbuf, A, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
+        } else if (aligned && kmax <= 8 && (size_t)m * 8 * sizeof(float4) <= VK_SMEM_BUDGET && !h->recon_generic) {
             if (kmax <= 2)
                 rc = launch_formv_smallk<2>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
             else if (kmax <= 4)
@@ -833,6 +837,9 @@ int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const 
         if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, B, m, n, kmax, out);
         return launch_recon_smallk<8>(h, U, S, Vt, B, m, n, kmax, out);
     }
+    if (h->gemm_impl == 0 && vk_cgemm_tc_supported(m, n, kmax) &&
+        ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0))
+        return vk_launch_recon_tc(h, U, S, Vt, ranks, out, B, m, n, kmax);
     ReconOp op{U, S, Vt, ranks, out, m, n, kmax};
     return cgemm_launch<64, 64, 4, 4, 8>(h, op, B);
 }
