@@ -8,6 +8,7 @@
 
 #define VK_SMEM_BUDGET (200 * 1024)  // dynamic shared memory we allow one CTA to ask for
 #define VK_MAX_R 2048                // largest min(m, n) the selection kernel sorts
+#define VK_HOST_CHUNKS 4             // sub-batches the *_host entry points pipeline copies and compute over
 #define VK_MAX_GROUPS 4              // independent matrix groups (streams) the Jacobi driver overlaps
 
 struct vk_context {
@@ -32,6 +33,8 @@ struct vk_context {
     cudaStream_t sub[VK_MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t sub_ev[VK_MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t host_ev[2 * VK_HOST_CHUNKS + 1] = {};
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
