@@ -283,3 +283,45 @@ def test_properties_at_kat7_config_size(eng, torch):
     for i, b in enumerate((0, 57, 111)):
         parity.check_factors(Ah[i], U[b].cpu().numpy(), S[b].cpu().numpy(), Vt[b].cpu().numpy(), k,
                              compressionrank=k, label=f"kat7 b={b}")
+
+
+# ---------------------------------------------------------------------------------------- fixed-rank fast path
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_fixed_rank_fast_path_matches_oracle_and_full_solver(eng, torch, k):
+    """Blocked subspace iteration (compressionrank <= 4): signal-dominated matrices are solved by it, noise-dominated
+    ones fall back to the full Jacobi solver inside the same call; both must satisfy the oracle tolerances and agree
+    with the full solver."""
+    A = _device_cube(eng, torch, 6, 4, 256, 1024, nbl_total=28, bl_offset=20)
+    try:
+        eng.set_option("topk", 1)
+        Uf, Sf, Vf, rf, _ = eng.compress(A, compressionrank=k)
+        eng.set_option("topk", 0)
+        U, S, Vt, ranks, stats = eng.compress(A, compressionrank=k)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("topk", 0)
+    st = stats.cpu().numpy()
+    assert np.all(st[:, 3] == 1)
+    np.testing.assert_allclose(S.cpu().numpy(), Sf.cpu().numpy(), rtol=2e-6)
+    a = A.cpu().numpy()
+    Uh, Sh, Vh = U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy()
+    for b in (0, 1, 3, 12, 13, 23):
+        parity.check_factors(a[b], Uh[b], Sh[b], Vh[b], k, compressionrank=k, label=f"fast path k={k} b={b}")
+        tot = float(np.sum(np.abs(a[b].astype(np.complex128)) ** 2))
+        assert abs(st[b, 0] - tot) <= 1e-4 * tot                 # ||A||_F^2 comes from the Gram trace on this path
+
+
+def test_fast_path_leaves_hard_spectra_to_the_full_solver(eng, torch):
+    """Flat spectrum (pure noise) and an exactly rank-2 matrix with compressionrank=3: no gap at the cut, the iteration
+    must give up (or certify) and the result must still be right."""
+    from visco_b200.compress_ms import apply_svd
+    rng = np.random.default_rng(3)
+    noise = (rng.standard_normal((128, 512)) + 1j * rng.standard_normal((128, 512))).astype(np.complex64)
+    U, S, Vt = apply_svd(noise, compressionrank=3)
+    parity.check_factors(noise, U, S, Vt, 3, compressionrank=3, label="fast path on noise")
+    lo = ((rng.standard_normal((160, 2)) + 1j * rng.standard_normal((160, 2))) @
+          (rng.standard_normal((2, 400)) + 1j * rng.standard_normal((2, 400)))).astype(np.complex64)
+    U, S, Vt = apply_svd(lo, compressionrank=3)
+    assert S[2] <= 1e-3 * S[0]
+    rec = (U * S) @ Vt
+    assert np.linalg.norm(lo - rec) <= 1e-5 * np.linalg.norm(lo)

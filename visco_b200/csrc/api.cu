@@ -156,7 +156,10 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         tm.mark(0);
         if (!gram_done && (rc = gram_stage(h, A, B, m, n, W, gscale, nonfinite))) return rc;
         tm.mark(1);
-        if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active))) return rc;
+        // fixed small rank: blocked subspace iteration first; the full Jacobi solver only sees what it left unsolved
+        const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
+        if (fast && (rc = vk_launch_topk(h, W, B, r, fixed_rank, done, sweeps))) return rc;
+        if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active, fast))) return rc;
         tm.mark(2);
         if ((rc = vk_launch_select(h, W, B, r, p.ldot, p.ld, gscale, 1, fixed_rank, decorrelation, kmax, perm, inv, S,
                                    ranks, stats, sweeps, done)))
@@ -279,6 +282,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_bsz = (int)v;
     else if (k == "stage_timing")
         h->stage_timing = (int)v;
+    else if (k == "topk")
+        h->topk = (int)v;
     else if (k == "gemm_impl")
         h->gemm_impl = (int)v;
     else if (k == "recon_generic")

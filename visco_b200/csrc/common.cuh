@@ -37,6 +37,7 @@ struct vk_context {
     cudaEvent_t host_ev[2 * VK_HOST_CHUNKS + 1] = {};
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
+    int topk = 0;            // 0 = auto (subspace iteration for compressionrank <= 4), 1 = full Jacobi only, 2 = up to rank 8
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
@@ -101,8 +102,11 @@ struct JacobiPlan {
 JacobiPlan vk_jacobi_plan(const vk_context* h, int r, int ldot, int ltot);
 
 // W in/out; offmax/done/sweeps are per-matrix device arrays of length B (int32 / float bits), active is 1 int.
+// preset_done: done_dev / sweeps_dev already hold the verdict of the fixed-rank fast path (1 = solved, skip)
 int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32_t* sweeps_dev, int32_t* done_dev,
-                     unsigned* offmax_dev, int32_t* active_dev);
+                     unsigned* offmax_dev, int32_t* active_dev, bool preset_done = false);
+bool vk_topk_supported(int r, int fixed_rank, bool force);
+int vk_launch_topk(vk_context* h, float2* W, int B, int r, int fixed_rank, int32_t* done_dev, int32_t* sweeps_dev);
 
 int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int side, float2* W);
 int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float2* W);

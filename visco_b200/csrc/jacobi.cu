@@ -595,16 +595,32 @@ JacobiPlan vk_jacobi_plan(const vk_context* h, int r, int ldot, int ltot) {
     return p;
 }
 
+__global__ void count_active_kernel(int B, const int32_t* __restrict__ done, int32_t* __restrict__ active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && !done[b]) atomicAdd(active, 1);
+}
+
 int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32_t* sweeps_dev, int32_t* done_dev,
-                     unsigned* offmax_dev, int32_t* active_dev) {
+                     unsigned* offmax_dev, int32_t* active_dev, bool preset_done) {
     if (B <= 0) return VK_OK;
     if (p.smem > VK_SMEM_BUDGET + 4096)
         return vk_fail(h, VK_EINVAL, "jacobi: a pair of vectors does not fit shared memory (matrix too large)");
     cudaStream_t st = h->stream;
     VK_CUDA(h, cudaFuncSetAttribute(jacobi_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    VK_CUDA(h, cudaMemsetAsync(sweeps_dev, 0, sizeof(int32_t) * B, st));
-    VK_CUDA(h, cudaMemsetAsync(done_dev, 0, sizeof(int32_t) * B, st));
+    if (!preset_done) {
+        VK_CUDA(h, cudaMemsetAsync(sweeps_dev, 0, sizeof(int32_t) * B, st));
+        VK_CUDA(h, cudaMemsetAsync(done_dev, 0, sizeof(int32_t) * B, st));
+    }
     VK_CUDA(h, cudaMemsetAsync(offmax_dev, 0, sizeof(unsigned) * B, st));
+    if (preset_done) {
+        // the fast path may have solved everything: one poll instead of a sweep of empty launches
+        VK_CUDA(h, cudaMemsetAsync(active_dev, 0, sizeof(int32_t), st));
+        count_active_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, done_dev, active_dev);
+        VK_LAUNCH_CHECK(h);
+        VK_CUDA(h, cudaMemcpyAsync(h->h_poll, active_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VK_CUDA(h, cudaStreamSynchronize(st));
+        if (h->h_poll[0] == 0) return VK_OK;
+    }
     // fp32 inner products of length ldot carry relative noise ~ sqrt(ldot) * 2^-24 (LAPACK xGESVJ uses the same
     // scale for its threshold): never rotate below it, and call a sweep converged when every off-diagonal it met
     // was below max(user tol, 4 * noise) — the rotations of that sweep then leave the matrix at the noise floor.

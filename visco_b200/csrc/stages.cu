@@ -260,7 +260,8 @@ select_kernel(const float2* __restrict__ W, int r, int ldot, int ld, const float
             tot += e;
             if (c < k) kept += e;
         }
-        stats[4 * b + 0] = (float)tot;
+        // Gram path: ||A||_F^2 is the trace of the Gram matrix (exact even when only the leading vectors were computed)
+        stats[4 * b + 0] = (mode_gram == 1) ? g * (float)r : (float)tot;
         stats[4 * b + 1] = (float)kept;
         stats[4 * b + 2] = (float)sweeps[b];
         stats[4 * b + 3] = (float)done[b];
