@@ -20,11 +20,11 @@
 // {32, 16, 8, 1} lands as 8 groups of 16 rows x 128 bytes), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11
 // converters (A: split in place; B: un-swizzle the raw row, optionally scale it by S[c], write rows 2k / 2k+1 of the
 // MN-major SWIZZLE_128B_BASE32B operand, hi and lo) and promoters / epilogue.
-#include <cuda.h>
-
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+using namespace tc;
 
 constexpr int TILE_M = 128;
 constexpr int TILE_NC = 128;              // complex output columns per tile = 256 floats = MMA N
@@ -45,101 +45,6 @@ constexpr int CHUNK_KB = 4;
 
 enum { MODE_FORMV = 0, MODE_RECON = 1 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-// K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// MN-major operand. For 32-bit (tf32) MN-major data the only layout the tensor core accepts is SWIZZLE_128B_BASE32B
-// (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type 1): 32 MN elements (128 bytes) contiguous per contraction row, atoms
-// of FOUR contraction rows (512 bytes), and inside an atom the 32-byte chunk index is XOR-ed with the row index
-// (Swizzle<2,5,2> on byte addresses). Leading byte offset = distance between 32-element MN groups, stride byte offset =
-// distance between 4-row contraction groups (make_umma_desc<Major::MN>).
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-struct Split4 {
-    float4 hi, lo;
-};
-__device__ __forceinline__ Split4 split4(float4 v) {
-    Split4 s;
-    s.hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    s.lo = make_float4(to_tf32(v.x - s.hi.x), to_tf32(v.y - s.hi.y), to_tf32(v.z - s.hi.z), to_tf32(v.w - s.hi.w));
-    return s;
-}
 // (r0, i0, r1, i1) -> (-i0, r0, -i1, r1) : the row that multiplies the imaginary part of the A operand
 __device__ __forceinline__ float4 rot90(float4 v) { return make_float4(-v.y, v.x, -v.w, v.z); }
 
@@ -243,7 +148,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // D = f32, A = B = tf32, A K-major, B MN-major (bit 16), N = 256, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = idesc_tf32(128, 256, true);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % NSTAGE;
                 const uint32_t use = kb / NSTAGE;
@@ -256,14 +161,14 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                const uint64_t a_hi = desc_kmajor(st + OFF_A_HI), a_lo = desc_kmajor(st + OFF_A_LO);
+                const uint64_t a_hi = desc_kmajor_sw128(st + OFF_A_HI), a_lo = desc_kmajor_sw128(st + OFF_A_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {  // 4 MMAs of K = 8 floats per K-block of 32
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);
                     // B: contraction rows 8k .. 8k+7 of every 32-float group: atom k of each group
-                    const uint64_t b_hi = desc_mnmajor(st + OFF_B_HI + k * 1024, 2 * KB_C * 128, 512);
-                    const uint64_t b_lo = desc_mnmajor(st + OFF_B_LO + k * 1024, 2 * KB_C * 128, 512);
+                    const uint64_t b_hi = desc_mnmajor_sw128_32b(st + OFF_B_HI + k * 1024, 2 * KB_C * 128, 512);
+                    const uint64_t b_lo = desc_mnmajor_sw128_32b(st + OFF_B_LO + k * 1024, 2 * KB_C * 128, 512);
                     umma_tf32(d, a_lo + adv, b_hi, idesc, !(first && k == 0));
                     umma_tf32(d, a_hi + adv, b_lo, idesc, 1);
                     umma_tf32(d, a_hi + adv, b_hi, idesc, 1);
@@ -364,24 +269,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-    return fn;
-}
-
 // A operand: P[b][rows][kc] complex, K-major: real view dims (2*kc, rows, B)
 int make_map_a(vk_context* h, CUtensorMap* map, const float2* P, int rows, int kc, int nb) {
-    PFN_encodeTiled enc = get_encode();
+    PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     const cuuint64_t dims[3] = {(cuuint64_t)2 * kc, (cuuint64_t)rows, (cuuint64_t)nb};
     const cuuint64_t strides[2] = {(cuuint64_t)2 * kc * 4, (cuuint64_t)rows * 2 * kc * 4};
@@ -395,7 +285,7 @@ int make_map_a(vk_context* h, CUtensorMap* map, const float2* P, int rows, int k
 }
 // B operand: Q[b][krows][nc] complex, N contiguous: view (32 floats, krows, 2*nc/32 groups, B); box {32, 16, 8, 1}
 int make_map_b(vk_context* h, CUtensorMap* map, const float2* Q, int krows, int nc, int nb) {
-    PFN_encodeTiled enc = get_encode();
+    PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     const cuuint64_t dims[4] = {32, (cuuint64_t)krows, (cuuint64_t)(2 * nc / 32), (cuuint64_t)nb};
     const cuuint64_t strides[3] = {(cuuint64_t)2 * nc * 4, 128, (cuuint64_t)krows * 2 * nc * 4};

@@ -67,9 +67,6 @@ static inline int vk_fail(vk_context* h, int code, const std::string& msg) {
 }
 
 // ---- small device helpers ---------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
 // acc += a * b
 __device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {
     acc.x = fmaf(a.x, b.x, acc.x);

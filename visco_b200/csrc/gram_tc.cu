@@ -20,11 +20,11 @@
 // hi/lo and the swapped copy, in place, swizzle-agnostic because the split is element-wise within 16-byte chunks)
 // and promoters (tcgen05.ld of finished chunks -> register accumulators -> global at the end). The converter warps
 // raise their register budget with setmaxnreg (128 accumulators per thread); the other warps give theirs up.
-#include <cuda.h>
-
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+using namespace tc;
 
 constexpr int TILE = 128;             // rows of a tile (both I and J)
 constexpr int KB_FLOATS = 32;         // K-block: 32 floats = 128 bytes = one SWIZZLE_128B row
@@ -41,83 +41,6 @@ constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
 constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulators (re | im), ping-pong
 constexpr int CHUNK_KB = 4;           // K-blocks per TMEM accumulation chain (4 x 12 = 48 MMAs)
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor fields)
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address            bits [0,14)
-    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major) bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset       bits [32,46)
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-
-// hi/lo split of one 16-byte chunk
-struct Split4 {
-    float4 hi, lo;
-};
-__device__ __forceinline__ Split4 split4(float4 v) {
-    Split4 s;
-    s.hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-    s.lo = make_float4(to_tf32(v.x - s.hi.x), to_tf32(v.y - s.hi.y), to_tf32(v.z - s.hi.z), to_tf32(v.w - s.hi.w));
-    return s;
-}
 // (r0, i0, r1, i1) -> (i0, -r0, i1, -r1)
 __device__ __forceinline__ float4 swap_neg(float4 v) { return make_float4(v.y, -v.x, v.w, -v.z); }
 
@@ -214,7 +137,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
         // ===================== MMA issuer =====================
         if (lane == 0) {
             // instruction descriptor: D = f32, A = B = tf32, K-major both, N = 256, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = idesc_tf32(128, 256, false);
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % NSTAGE;
                 const uint32_t use = kb / NSTAGE;
@@ -227,8 +150,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                const uint64_t a_hi = make_sw128_desc(st + OFF_A_HI), a_lo = make_sw128_desc(st + OFF_A_LO);
-                const uint64_t b_hi = make_sw128_desc(st + OFF_B_HI), b_lo = make_sw128_desc(st + OFF_B_LO);
+                const uint64_t a_hi = desc_kmajor_sw128(st + OFF_A_HI), a_lo = desc_kmajor_sw128(st + OFF_A_LO);
+                const uint64_t b_hi = desc_kmajor_sw128(st + OFF_B_HI), b_lo = desc_kmajor_sw128(st + OFF_B_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
                 for (int k = 0; k < KB_FLOATS / 8; ++k) {
@@ -311,22 +234,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
     }
 }
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-    return fn;
-}
-
 }  // namespace
 
 bool vk_gram_tc_supported(int m, int n, int side) {
@@ -335,7 +242,7 @@ bool vk_gram_tc_supported(int m, int n, int side) {
 }
 
 int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float2* W) {
-    PFN_encodeTiled encode = get_encode();
+    PFN_encodeTiled encode = get_encode_tiled();
     if (!encode) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     const int T = (m + TILE - 1) / TILE;
     const int tiles = T * (T + 1) / 2;

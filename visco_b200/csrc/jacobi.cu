@@ -377,12 +377,12 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
 }
 
 template <int EPL>
-int launch_cross(vk_context* h, float2* W, size_t mat_stride, const JacobiPlan& p, int round, unsigned nblocks,
-                 float tol2_rot, unsigned* offmax, const int32_t* done) {
+int launch_cross(vk_context* h, cudaStream_t st, float2* W, size_t mat_stride, const JacobiPlan& p, int round,
+                 unsigned nblocks, float tol2_rot, unsigned* offmax, const int32_t* done) {
     const size_t smem = (size_t)p.bsz * 32 * EPL * sizeof(float2) + (size_t)p.bsz * 8;
     if (smem > 48 * 1024)  // per-device attribute; cheap enough to set on every launch
         VK_CUDA(h, cudaFuncSetAttribute(jacobi_cross_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    jacobi_cross_kernel<EPL><<<nblocks, 32 * p.bsz, smem, h->stream>>>(W, mat_stride, p.ld, p.r, p.bsz, p.nb, round,
+    jacobi_cross_kernel<EPL><<<nblocks, 32 * p.bsz, smem, st>>>(W, mat_stride, p.ld, p.r, p.bsz, p.nb, round,
                                                                         tol2_rot, offmax, done);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
@@ -397,14 +397,14 @@ int cross_epl(const JacobiPlan& p) {
     return 0;
 }
 
-int launch_cross_dispatch(vk_context* h, int epl, float2* W, size_t mat_stride, const JacobiPlan& p, int round,
-                          unsigned nblocks, float tol2_rot, unsigned* offmax, const int32_t* done) {
+int launch_cross_dispatch(vk_context* h, cudaStream_t st, int epl, float2* W, size_t mat_stride, const JacobiPlan& p,
+                          int round, unsigned nblocks, float tol2_rot, unsigned* offmax, const int32_t* done) {
     switch (epl) {
-        case 4: return launch_cross<4>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
-        case 6: return launch_cross<6>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
-        case 8: return launch_cross<8>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
-        case 12: return launch_cross<12>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
-        case 16: return launch_cross<16>(h, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
+        case 4: return launch_cross<4>(h, st, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
+        case 6: return launch_cross<6>(h, st, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
+        case 8: return launch_cross<8>(h, st, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
+        case 12: return launch_cross<12>(h, st, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
+        case 16: return launch_cross<16>(h, st, W, mat_stride, p, round, nblocks, tol2_rot, offmax, done);
     }
     return vk_fail(h, VK_EINVAL, "jacobi: no cross kernel for this size");
 }
@@ -689,11 +689,8 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
                                                                 sweeps_dev + b0);
             VK_LAUNCH_CHECK(h);
             for (int round = 0; round < p.nb - 1; ++round) {
-                cudaStream_t keep = h->stream;
-                h->stream = sg;
-                const int rc = launch_cross_dispatch(h, epl, Wg, mat_stride, p, round, nblk, tol2_rot, offmax_dev + b0,
+                const int rc = launch_cross_dispatch(h, sg, epl, Wg, mat_stride, p, round, nblk, tol2_rot, offmax_dev + b0,
                                                      done_dev + b0);
-                h->stream = keep;
                 if (rc) return rc;
             }
         } else {
