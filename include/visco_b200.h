@@ -124,6 +124,16 @@ int vk_gather_baselines(vk_handle h, const void* data_dev, int nchan, int ncorr,
 int vk_scatter_baselines(vk_handle h, const void* cube_dev, int nchan, int ncorr, const int32_t* row_idx_dev, int nbl,
                          int m, const int32_t* corr_sel_dev, int ncs, int stack, void* data_dev);
 
+/* ---- flags ---------------------------------------------------------------------------------- */
+/* np.packbits(flags, axis=None) / np.unpackbits(packed, count=n) on device, big bit order (compress_ms.py:478-483,
+ * decompress_ms.py:240-246). flags are one byte per element (numpy bool). packed has (n + 7) / 8 bytes. */
+int vk_packbits(vk_handle h, const uint8_t* flags_dev, size_t n, uint8_t* packed_dev);
+int vk_unpackbits(vk_handle h, const uint8_t* packed_dev, size_t n, uint8_t* flags_dev);
+/* In-place da.where(FLAG, replacement, data) over n complex64 visibilities: replacement = model_dev[e] when model_dev is
+ * not NULL (use_model_data, compress_ms.py:531-542), else the constant value_re + i value_im (flagvalue, :549-562). */
+int vk_flag_replace(vk_handle h, void* data_dev, const uint8_t* flags_dev, const void* model_dev, float value_re,
+                    float value_im, size_t n);
+
 /* ---- benchmark generator (SURVEY.md section 8d model), on device ------------------------------------------ */
 /* A[b] for b = baseline * ncorr + corr; global baseline index = bl_offset + baseline out of nbl_total. */
 int vk_synth_fill(vk_handle h, void* A_dev, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,

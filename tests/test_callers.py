@@ -83,4 +83,6 @@ def test_driver_errors_before_any_gpu_work(tmp_path):
     with pytest.raises(ValueError):
         compress_full_ms(ms_path=bundle, **{**kw, "compressor": "lzma"})                 # reference :51
     with pytest.raises(NotImplementedError):
-        compress_full_ms(ms_path=bundle, flagvalue=1, **kw)
+        compress_full_ms(ms_path=bundle, flag_estimate=True, **kw)                       # griddata estimator: out of scope
+    with pytest.raises(ValueError):
+        compress_full_ms(ms_path=bundle, flagvalue="not-a-number", **kw)                 # reference :549-558

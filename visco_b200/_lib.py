@@ -32,6 +32,9 @@ SIGNATURES = {
     "vk_gram_uses_tcgen05": (_i, [_i, _i, _i]),
     "vk_gather_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "vk_scatter_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "vk_packbits": (_i, [_vp, _vp, _sz, _vp]),
+    "vk_unpackbits": (_i, [_vp, _vp, _sz, _vp]),
+    "vk_flag_replace": (_i, [_vp, _vp, _vp, _vp, _f, _f, _sz]),
     "vk_synth_fill": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _u64]),
     "vk_launch_count": (C.c_int64, [_vp]),
     "vk_last_stage_ms": (_i, [_vp, C.POINTER(_f)]),

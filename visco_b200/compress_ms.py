@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import LOG
 from .engine import get_engine
 
 
@@ -97,7 +98,7 @@ def _leaf_jobs(vis, baseline_batch, correlation, correlation_optimized):
 
 def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_optimized=False, decorrelation=None,
                      compressionrank=None, outcolumn="COMPRESSED_DATA", compressor="zstd", level=4, batch_size=20,
-                     antennas=None):
+                     antennas=None, data_dev=None):
     """Compress every (baseline, correlation) matrix of `vis` (a visco_b200.msdata.VisData) and write the leaf tree
     ``<zarr>/MAIN/<outcolumn>/<ANT1>&<ANT2>/<corr>/`` (reference compress_visdata, compress_ms.py:389-703).
 
@@ -128,7 +129,8 @@ def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_opt
     baselines = vis.baselines(antennas)
     if not leaf_names:
         return 0
-    data_dev = torch.from_numpy(vis.data).to(dev)
+    if data_dev is None:
+        data_dev = torch.from_numpy(vis.data).to(dev)
     processed = 0
     for batch in batch_baselines(baselines, batch_size):
         by_m = {}
@@ -166,8 +168,9 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
                      compressionrank: int = None, flagvalue: int = None, antennas: list = None):
     """Same keyword arguments as the reference's compress_full_ms (compress_ms.py:782-811). The dask-cluster arguments
     (nworkers, nthreads, memory_limit, direct_to_workers, dashboard_addr, host_addr, chunk_size_row) are accepted and
-    ignored: the batches run on the GPU of this process. Flag-value replacement (use_model_data / flag_estimate /
-    flagvalue, compress_ms.py:530-566) is outside the hot path and not implemented: passing them raises."""
+    ignored: the batches run on the GPU of this process. Flags are bit-packed into the FLAGS / FLAGS_ROW groups and
+    flagged visibilities are replaced by model data or by a constant on the device (compress_ms.py:478-483, 530-562);
+    the scipy-griddata estimator (flag_estimate, compress_ms.py:197-292) is out of scope and raises."""
     import os
     import shutil
 
@@ -175,8 +178,16 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
     from .zarr_leaf import write_group
     if not os.path.exists(ms_path):
         raise ValueError(f"MS path {ms_path} does not exist.")                     # reference :876-877
-    if use_model_data or flag_estimate or flagvalue is not None:
-        raise NotImplementedError("flag replacement (use_model_data / flag_estimate / flagvalue) is out of scope")
+    if flag_estimate and not use_model_data:
+        raise NotImplementedError("flag_estimate (scipy griddata interpolation) is out of scope of this build")
+    if flagvalue and not use_model_data and isinstance(flagvalue, str):
+        try:                                                                       # reference :549-558
+            flagvalue = complex(flagvalue.replace(" ", ""))
+        except ValueError:
+            try:
+                flagvalue = float(flagvalue)
+            except ValueError:
+                raise ValueError(f"Invalid flagvalue '{flagvalue}'. Use a float or complex format like '1+1j'.")
     if compressor is not None:
         from .zarr_leaf import get_compressor
         get_compressor(compressor, level)                                          # ValueError for unknown names (:51)
@@ -193,6 +204,30 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
     write_group(os.path.join(zarr_path, "ANTENNA"), {"NAME": (np.array(vis.antenna_names, dtype="U"), ("row",))})
     write_group(os.path.join(zarr_path, "POLARIZATION"),
                 {"CORR_TYPE": (np.array([vis.corr_types], dtype=np.int32), ("row", "corr"))})
-    return compress_visdata(vis, zarr_path, correlation=correlation, correlation_optimized=correlation_optimized,
+    import torch
+    eng = get_engine()
+    dev = f"cuda:{eng.device}"
+    data_dev = torch.from_numpy(vis.data).to(dev)
+    # flags: bit-packed groups FLAGS / FLAGS_ROW (reference :478-483; FLAGS_ROW is the reference's spelling)
+    flag = vis.flag if vis.flag is not None else np.zeros(vis.data.shape, bool)
+    flag_row = vis.flag_row if vis.flag_row is not None else np.zeros(nrow, bool)
+    flag_dev = torch.from_numpy(flag).to(dev)
+    for group, packed in (("FLAGS", eng.packbits(flag_dev)), ("FLAGS_ROW", eng.packbits(torch.from_numpy(flag_row).to(dev)))):
+        p = packed.cpu().numpy()
+        write_group(os.path.join(zarr_path, group), {group: (p, ("row",)), "row": (np.arange(p.shape[0]), ("row",))})
+    # flagged-value replacement before the SVD (reference :530-566)
+    if use_model_data:
+        mod = vis.model_data
+        if model_data is not None and model_data != "MODEL_DATA":
+            mod = VisData.load(ms_path, column=model_data).data if str(ms_path).endswith(".npz") else None
+        if mod is None:
+            raise ValueError("use_model_data needs a MODEL_DATA column in the data set")
+        eng.flag_replace(data_dev, flag_dev, model=torch.from_numpy(np.ascontiguousarray(mod, np.complex64)).to(dev))
+    elif flagvalue:
+        LOG.warning(f"Replacing flagged data with {flagvalue} - may amplify noise")      # reference :560
+        eng.flag_replace(data_dev, flag_dev, value=complex(flagvalue))
+    else:
+        LOG.warning("No flag replacement specified - flagged data will not be replaced")  # reference :566
+    return compress_visdata(vis, zarr_path, data_dev=data_dev, correlation=correlation, correlation_optimized=correlation_optimized,
                             decorrelation=decorrelation, compressionrank=compressionrank, outcolumn=outcolumn,
                             compressor=compressor, level=level, batch_size=batch_size, antennas=antennas)

@@ -47,6 +47,33 @@ layout_kernel(float2* __restrict__ data, const int32_t* __restrict__ row_idx, co
     }
 }
 
+// ---- flags ------------------------------------------------------------------------------
+// np.packbits(flags, axis=None): 8 booleans per byte, first element in the MOST significant bit (bitorder 'big'),
+// tail padded with zeros (reference compress_ms.py:478-483); np.unpackbits(..., count=n) is the inverse
+// (reference decompress_ms.py:240-246). One thread per output byte, 8 coalesced-enough byte reads.
+__global__ void __launch_bounds__(256) packbits_kernel(const uint8_t* __restrict__ flags, size_t n, uint8_t* __restrict__ out) {
+    const size_t nb = (n + 7) / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned v = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const size_t e = i * 8 + j;
+            v = (v << 1) | ((e < n && flags[e]) ? 1u : 0u);
+        }
+        out[i] = (uint8_t)v;
+    }
+}
+__global__ void __launch_bounds__(256) unpackbits_kernel(const uint8_t* __restrict__ packed, size_t n, uint8_t* __restrict__ out) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        out[e] = (packed[e >> 3] >> (7 - (e & 7))) & 1u;
+}
+// da.where(FLAG, replacement, data) with a constant or a model column (reference compress_ms.py:530-562), in place
+__global__ void __launch_bounds__(256) flag_replace_kernel(float2* __restrict__ data, const uint8_t* __restrict__ flags,
+                                                           const float2* __restrict__ model, float2 value, size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        if (flags[e]) data[e] = model ? model[e] : value;
+}
+
 }  // namespace
 
 static int layout_launch(vk_context* h, bool gather, float2* data, const int32_t* row_idx, const int32_t* corr_sel,
@@ -70,7 +97,45 @@ static int layout_launch(vk_context* h, bool gather, float2* data, const int32_t
     return VK_OK;
 }
 
+static unsigned flag_grid(size_t n) {
+    size_t g = (n + 255) / 256;
+    return (unsigned)(g > 148 * 16 ? 148 * 16 : (g ? g : 1));
+}
+
 extern "C" {
+
+int vk_packbits(vk_handle h, const uint8_t* flags_dev, size_t n, uint8_t* packed_dev) {
+    if (!h) return VK_EINVAL;
+    if (n == 0) return VK_OK;
+    if (!flags_dev || !packed_dev) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    packbits_kernel<<<flag_grid((n + 7) / 8), 256, 0, h->stream>>>(flags_dev, n, packed_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_unpackbits(vk_handle h, const uint8_t* packed_dev, size_t n, uint8_t* flags_dev) {
+    if (!h) return VK_EINVAL;
+    if (n == 0) return VK_OK;
+    if (!flags_dev || !packed_dev) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    unpackbits_kernel<<<flag_grid(n), 256, 0, h->stream>>>(packed_dev, n, flags_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_flag_replace(vk_handle h, void* data_dev, const uint8_t* flags_dev, const void* model_dev, float value_re,
+                    float value_im, size_t n) {
+    if (!h) return VK_EINVAL;
+    if (n == 0) return VK_OK;
+    if (!data_dev || !flags_dev) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    flag_replace_kernel<<<flag_grid(n), 256, 0, h->stream>>>(static_cast<float2*>(data_dev), flags_dev,
+                                                             static_cast<const float2*>(model_dev),
+                                                             make_float2(value_re, value_im), n);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
 
 int vk_gather_baselines(vk_handle h, const void* data_dev, int nchan, int ncorr, const int32_t* row_idx_dev, int nbl,
                         int m, const int32_t* corr_sel_dev, int ncs, int stack, void* A_dev) {

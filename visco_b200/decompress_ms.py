@@ -161,8 +161,18 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
             corr_sel = torch.tensor([list(planes[t[4]]) for t in ts], dtype=torch.int32, device=dev)
             eng.scatter_baselines(rec, out_dev, row_idx, corr_sel, stack)
     out = out_dev.cpu().numpy()
+    # flags: unpack the bit-packed FLAGS / FLAGS_ROW groups (reference :240-246)
+    flag = flag_row = None
+    from .zarr_leaf import read_array
+    if os.path.isdir(os.path.join(zarr_path, "FLAGS", "FLAGS")):
+        packed = torch.from_numpy(read_array(os.path.join(zarr_path, "FLAGS", "FLAGS")).astype(np.uint8)).to(dev)
+        flag = eng.unpackbits(packed, out.size).cpu().numpy().astype(bool).reshape(out.shape)
+    if os.path.isdir(os.path.join(zarr_path, "FLAGS_ROW", "FLAGS_ROW")):
+        packed = torch.from_numpy(read_array(os.path.join(zarr_path, "FLAGS_ROW", "FLAGS_ROW")).astype(np.uint8)).to(dev)
+        flag_row = eng.unpackbits(packed, out.shape[0]).cpu().numpy().astype(bool)
     corr_types = [9, 10, 11, 12][:ncorr] if ncorr <= 4 else list(range(ncorr))
-    return VisData(data=out, antenna1=ant1, antenna2=ant2, antenna_names=antnames, corr_types=corr_types, rowid=rowid)
+    return VisData(data=out, antenna1=ant1, antenna2=ant2, antenna_names=antnames, corr_types=corr_types, rowid=rowid,
+                   flag=flag, flag_row=flag_row)
 
 
 def open_dataset(zarr_path: str, column: str = "COMPRESSED_DATA", batch_size: int = 50):

@@ -184,6 +184,41 @@ class Engine:
         self._check(rc, "vk_scatter_baselines")
         return data
 
+    # flags
+    def packbits(self, flags):
+        """np.packbits(flags, axis=None) on device: flags is a CUDA bool/uint8 tensor of any shape."""
+        torch = _torch()
+        f = flags.contiguous().view(torch.uint8).reshape(-1)
+        out = torch.empty(((f.numel() + 7) // 8,), dtype=torch.uint8, device=f.device)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_packbits(self.h, self._ptr(f), f.numel(), self._ptr(out))
+        self._check(rc, "vk_packbits")
+        return out
+
+    def unpackbits(self, packed, count):
+        """np.unpackbits(packed, count=count) on device -> CUDA uint8 tensor [count]."""
+        torch = _torch()
+        out = torch.empty((int(count),), dtype=torch.uint8, device=packed.device)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_unpackbits(self.h, self._ptr(packed.contiguous()), int(count), self._ptr(out))
+        self._check(rc, "vk_unpackbits")
+        return out
+
+    def flag_replace(self, data, flags, model=None, value=0j):
+        """In place: data = where(flags, model or value, data) (reference compress_ms.py:530-562)."""
+        torch = _torch()
+        f = flags.contiguous().view(torch.uint8)
+        assert data.is_contiguous() and f.numel() == data.numel() and (model is None or model.shape == data.shape)
+        v = complex(value)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_flag_replace(self.h, self._ptr(data), self._ptr(f), self._ptr(model.contiguous()) if model is not None else None,
+                                          float(v.real), float(v.imag), data.numel())
+        self._check(rc, "vk_flag_replace")
+        return data
+
     # stage-level (tests / profiling)
     def gram(self, A, impl=0):
         torch = _torch()

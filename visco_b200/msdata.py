@@ -31,6 +31,8 @@ class VisData:
     corr_types: list = field(default_factory=lambda: [9, 10, 11, 12])   # casacore enums of the corr axis
     rowid: np.ndarray | None = None  # [row] int64
     flag: np.ndarray | None = None   # [row, chan, corr] bool (optional)
+    flag_row: np.ndarray | None = None       # [row] bool (optional)
+    model_data: np.ndarray | None = None     # [row, chan, corr] complex64 (optional; flag replacement source)
     column: str = "DATA"
 
     def __post_init__(self):
@@ -49,12 +51,24 @@ class VisData:
         self.corr_types = [int(c) for c in self.corr_types]
         if len(self.corr_types) != self.data.shape[2]:
             raise ValueError("corr_types must describe the correlation axis")
+        if self.flag is not None:
+            self.flag = np.ascontiguousarray(self.flag, dtype=bool)
+            if self.flag.shape != self.data.shape:
+                raise ValueError("FLAG must have the shape of the visibility column")
+        if self.flag_row is not None:
+            self.flag_row = np.ascontiguousarray(self.flag_row, dtype=bool)
+        if self.model_data is not None:
+            self.model_data = np.ascontiguousarray(self.model_data, dtype=np.complex64)
+            if self.model_data.shape != self.data.shape:
+                raise ValueError("MODEL_DATA must have the shape of the visibility column")
 
     # --------------------------------------------------------------------------------------------- persistence
     def save(self, path: str):
         np.savez_compressed(path, DATA=self.data, ANTENNA1=self.antenna1, ANTENNA2=self.antenna2, ROWID=self.rowid,
                             ANTENNA_NAME=np.array(self.antenna_names), CORR_TYPE=np.array(self.corr_types, np.int32),
-                            **({"FLAG": self.flag} if self.flag is not None else {}))
+                            **({"FLAG": self.flag} if self.flag is not None else {}),
+                            **({"FLAG_ROW": self.flag_row} if self.flag_row is not None else {}),
+                            **({"MODEL_DATA": self.model_data} if self.model_data is not None else {}))
 
     @classmethod
     def load(cls, path: str, column: str = "DATA", scan=None, fieldid=None, ddid=None):
@@ -66,7 +80,9 @@ class VisData:
                 key = column if column in z.files else "DATA"
                 return cls(data=z[key], antenna1=z["ANTENNA1"], antenna2=z["ANTENNA2"],
                            antenna_names=list(z["ANTENNA_NAME"]), corr_types=list(z["CORR_TYPE"]), rowid=z["ROWID"],
-                           flag=z["FLAG"] if "FLAG" in z.files else None, column=column)
+                           flag=z["FLAG"] if "FLAG" in z.files else None,
+                           flag_row=z["FLAG_ROW"] if "FLAG_ROW" in z.files else None,
+                           model_data=z["MODEL_DATA"] if "MODEL_DATA" in z.files else None, column=column)
         if not os.path.exists(path):
             raise ValueError(f"Measurement Set {path} does not exist")     # reference compress_ms.py:876-877
         try:
