@@ -325,3 +325,81 @@ def test_fast_path_leaves_hard_spectra_to_the_full_solver(eng, torch):
     assert S[2] <= 1e-3 * S[0]
     rec = (U * S) @ Vt
     assert np.linalg.norm(lo - rec) <= 1e-5 * np.linalg.norm(lo)
+
+
+# ---------------------------------------------------------------------------------------- raw C ABI behaviour
+def test_c_abi_status_codes_and_messages(eng, torch):
+    """Error convention of the boundary: integer status + vk_last_error, no exceptions across the ABI."""
+    import ctypes as C
+    from visco_b200 import _lib
+    lib = eng.lib
+    A = torch.zeros((2, 8, 8), dtype=torch.complex64, device="cuda:0")
+    U = torch.empty((2, 8, 8), dtype=torch.complex64, device="cuda:0")
+    S = torch.empty((2, 8), dtype=torch.float32, device="cuda:0")
+    Vt = torch.empty((2, 8, 8), dtype=torch.complex64, device="cuda:0")
+    rk = torch.empty((2,), dtype=torch.int32, device="cuda:0")
+    st = torch.empty((2, 4), dtype=torch.float32, device="cuda:0")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    call = lambda *a: lib.vk_compress_batched(eng.h, *a)
+    assert call(p(A), 2, 8, 8, 0, 0.0, 8, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_OK
+    assert call(None, 2, 8, 8, 0, 0.0, 8, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_EINVAL
+    assert b"null" in lib.vk_last_error(eng.h)
+    assert call(p(A), 2, 0, 8, 0, 0.0, 8, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_EINVAL        # m = 0
+    assert call(p(A), 2, 8, 8, 0, -0.5, 8, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_EINVAL      # decorrelation < 0
+    assert call(p(A), 2, 8, 8, 4, 0.0, 2, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_EINVAL       # kmax < rank
+    assert b"kmax" in lib.vk_last_error(eng.h)
+    assert call(p(A), 2, 8, 8, 0, 0.0, 9, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_EINVAL       # kmax > min(m, n)
+    assert call(p(A), 2, 8, 8, 0, 0.0, 8, p(U), p(S), p(Vt), p(rk), p(st), p(A), 16) == _lib.VK_EINVAL      # workspace too small
+    assert call(p(A), 0, 8, 8, 0, 0.0, 8, p(U), p(S), p(Vt), p(rk), p(st), None, 0) == _lib.VK_OK           # empty batch
+    assert lib.vk_set_option(eng.h, b"no_such_option", 1.0) == _lib.VK_EINVAL
+    assert lib.vk_reconstruct_batched(eng.h, p(U), p(S), p(Vt), None, 2, 8, 8, 0, p(A)) == _lib.VK_EINVAL   # kmax = 0
+    assert lib.vk_workspace_bytes(eng.h, 64, 512, 4096, 512) >= 64 * 512 * 512 * 8
+    big = torch.empty((1, 4, 4), dtype=torch.complex64, device="cuda:0")
+    assert lib.vk_svd_jacobi_small_batched(eng.h, p(big), 1, 4096, 4096, p(U), p(S), p(Vt), None) == _lib.VK_EINVAL
+
+
+def test_handles_are_independent_and_thread_safe(torch):
+    """One handle per host thread (SURVEY 8b threading): two engines on the same GPU used concurrently give the same
+    answer as a serial run; destroying one leaves the other usable."""
+    import threading
+    from visco_b200.engine import Engine, get_engine
+    base = get_engine(0)
+    A = _device_cube(base, torch, 4, 4, 128, 256)
+    ref = base.compress(A, compressionrank=5)[1].cpu().numpy()
+    engines = [Engine(0), Engine(0)]
+    out = [None, None]
+
+    def work(i):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                out[i] = engines[i].compress(A, compressionrank=5)[1]
+            s.synchronize()
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(2):
+        np.testing.assert_allclose(out[i].cpu().numpy(), ref, rtol=1e-6)
+    engines[0].close()
+    np.testing.assert_allclose(engines[1].compress(A, compressionrank=5)[1].cpu().numpy(), ref, rtol=1e-6)
+    engines[1].close()
+
+
+def test_internal_scheduling_options_do_not_change_results(eng, torch):
+    """chunking, stream groups and the generic Jacobi kernels are performance knobs only."""
+    A = _device_cube(eng, torch, 3, 4, 192, 384)
+    base = eng.compress(A, decorrelation=0.97)
+    try:
+        for opts in ({"chunk": 5}, {"jacobi_groups": 1}, {"jacobi_groups": 4}, {"jacobi_generic": 1}, {"gram_impl": 1},
+                     {"gemm_impl": 1}):
+            for k_, v_ in opts.items():
+                eng.set_option(k_, v_)
+            got = eng.compress(A, decorrelation=0.97)
+            for k_ in opts:
+                eng.set_option(k_, 0)
+            assert torch.equal(got[3], base[3]), opts
+            assert float(((got[1] - base[1]).abs() / base[1].clamp_min(1e-20)).max()) < 2e-5, opts
+    finally:
+        for k_ in ("chunk", "jacobi_groups", "jacobi_generic", "gram_impl", "gemm_impl"):
+            eng.set_option(k_, 0)

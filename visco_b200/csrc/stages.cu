@@ -778,17 +778,20 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
         if ((rc = launch_cols(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
         FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
         const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16 == 0);
-        if (xbuf && h->gemm_impl == 0 && vk_cgemm_tc_supported(m, n, kmax)) {
+        if (xbuf && h->gemm_impl == 0 && kmax > 16 && vk_cgemm_tc_supported(m, n, kmax)) {
             // large rank: X = conj(U_k)^T / lambda materialised K-major, then the tcgen05 complex GEMM
             if ((rc = launch_rows(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 1, 1, xbuf, B))) return rc;
             rc = vk_launch_formv_tc(h, xbuf, A, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
-        } else if (aligned && kmax <= 8 && (size_t)m * 8 * sizeof(float4) <= VK_SMEM_BUDGET && !h->recon_generic) {
+        } else if (aligned && kmax <= 16 && (size_t)m * (kmax <= 8 ? 8 : 16) * sizeof(float4) <= VK_SMEM_BUDGET &&
+                   !h->recon_generic) {
             if (kmax <= 2)
                 rc = launch_formv_smallk<2>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
             else if (kmax <= 4)
                 rc = launch_formv_smallk<4>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
-            else
+            else if (kmax <= 8)
                 rc = launch_formv_smallk<8>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
+            else
+                rc = launch_formv_smallk<16>(h, A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
         } else if (kmax <= 8)
             rc = cgemm_launch<8, 256, 8, 2, 16>(h, op, B);
         else if (kmax <= 32)
@@ -833,12 +836,14 @@ int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const 
                           int m, int n, int kmax, float2* out) {
     // small rank: dedicated streaming kernel (factors are zero-padded beyond ranks[b], so kmax modes are summed)
     const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
-    if (aligned && kmax <= 8 && !h->recon_generic) {
+    // (k <= 16 stays below the FFMA2 limit of ~0.7 x HBM; the tcgen05 GEMM only wins from k ~ 20 on, measured)
+    if (aligned && kmax <= 16 && !h->recon_generic) {
         if (kmax <= 2) return launch_recon_smallk<2>(h, U, S, Vt, B, m, n, kmax, out);
         if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, B, m, n, kmax, out);
-        return launch_recon_smallk<8>(h, U, S, Vt, B, m, n, kmax, out);
+        if (kmax <= 8) return launch_recon_smallk<8>(h, U, S, Vt, B, m, n, kmax, out);
+        return launch_recon_smallk<16>(h, U, S, Vt, B, m, n, kmax, out);
     }
-    if (h->gemm_impl == 0 && vk_cgemm_tc_supported(m, n, kmax) &&
+    if (h->gemm_impl == 0 && kmax > 16 && vk_cgemm_tc_supported(m, n, kmax) &&
         ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0))
         return vk_launch_recon_tc(h, U, S, Vt, ranks, out, B, m, n, kmax);
     ReconOp op{U, S, Vt, ranks, out, m, n, kmax};
