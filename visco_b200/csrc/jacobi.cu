@@ -60,6 +60,25 @@ __device__ __forceinline__ void rotation_params(float a, float b, float zr, floa
     taz = copysignf(zg, d);  // norm transfer: a' = a - t|z|, b' = b + t|z|
 }
 
+// Same rotation in "fast Givens" form: returns c, 1/c and tau = w / c = z * sign(d) * g, so that the caller can apply
+//   x' = c (x - conj(tau) y) ,  y' = c (y + tau x)
+// and fold the common factor c into per-vector scale factors instead of multiplying every element by it.
+__device__ __forceinline__ void rotation_params_fast(float a, float b, float zr, float zi, float zz, float& c, float& invc,
+                                                     float& tr, float& ti, float& taz) {
+    const float d = 0.5f * (b - a);
+    const float q = fmaf(d, d, zz);
+    const float h = q * rsqrtf(q);
+    const float g = __fdividef(1.f, fabsf(d) + h);
+    const float zg = zz * g;
+    const float u = fmaf(zg, g, 1.f);
+    c = rsqrt_unit(u);
+    invc = u * c;  // sqrt(u)
+    const float tg = copysignf(g, d);
+    tr = zr * tg;
+    ti = zi * tg;
+    taz = copysignf(zg, d);
+}
+
 // sum zr and zi over the warp with 7 shuffles instead of 10: the first butterfly step leaves the zr partial sums in the
 // lower half-warp and the zi partial sums in the upper one
 __device__ __forceinline__ void warp_sum2(float& zr, float& zi, int lane) {
@@ -254,6 +273,7 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
     float* YI = YR + (size_t)bsz * L;                  // [bsz][L]
     float* nrm = YI + (size_t)bsz * L;                 // [bsz]
     int* gidx = reinterpret_cast<int*>(nrm + bsz);     // [bsz]
+    float* ysc = reinterpret_cast<float*>(gidx + bsz); // [2 * bsz] scale factor of each y and its reciprocal
     int bi, bj;
     rr_pair(nb, round, pslot, bi, bj);
     float2* Wb = W + (size_t)b * mat_stride;
@@ -289,10 +309,16 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
         if (lane == 0) {
             nrm[warp] = s;
             gidx[warp] = validy ? gy : -1;
+            ysc[2 * warp] = 1.f;
+            ysc[2 * warp + 1] = 1.f;
         }
     }
     __syncthreads();
 
+    // Fast Givens: the registers / shared memory hold x~ and y~ with x = ax x~, y = ay y~. A rotation becomes
+    // x~' = x~ - conj(tau) (ay/ax) y~ ,  y~' = y~ + tau (ax/ay) x~ ,  ax' = c ax ,  ay' = c ay   (8 instead of 12 packed FMAs
+    // per element pair); the scales (>= 0.707^16 within a launch) are multiplied back in when the vectors are stored.
+    float ax = 1.f, rax = 1.f;
     float mymax = 0.f;
     for (int q = 0; q < bsz; ++q) {
         int j = warp + q;
@@ -302,50 +328,55 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
             float* yip = YI + (size_t)j * L + 2 * lane;
             // y stays in registers between the inner product and the rotation. (Re-reading it from shared memory to fit
             // 2 CTAs/SM at EPL = 16 was measured: 64 registers with spills, Jacobi time 219 -> 383 ms. Rejected.)
-            constexpr bool KEEP_Y = true;
-            float2 yr[KEEP_Y ? NP : 1], yi[KEEP_Y ? NP : 1];
+            float2 yr[NP], yi[NP];
             float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f), R = make_float2(0.f, 0.f);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                const float2 vr = *reinterpret_cast<const float2*>(yrp + 64 * p);
-                const float2 vi = *reinterpret_cast<const float2*>(yip + 64 * p);
-                if (KEEP_Y) {
-                    yr[p] = vr;
-                    yi[p] = vi;
-                }
-                P = __ffma2_rn(xr[p], vr, P);  // z = x^H y : re = xr yr + xi yi ; im = xr yi - xi yr
-                P = __ffma2_rn(xi[p], vi, P);
-                Q = __ffma2_rn(xr[p], vi, Q);
-                R = __ffma2_rn(xi[p], vr, R);
+                yr[p] = *reinterpret_cast<const float2*>(yrp + 64 * p);
+                yi[p] = *reinterpret_cast<const float2*>(yip + 64 * p);
+                P = __ffma2_rn(xr[p], yr[p], P);  // z = x^H y : re = xr yr + xi yi ; im = xr yi - xi yr
+                P = __ffma2_rn(xi[p], yi[p], P);
+                Q = __ffma2_rn(xr[p], yi[p], Q);
+                R = __ffma2_rn(xi[p], yr[p], R);
             }
             float zr = P.x + P.y, zi = (Q.x + Q.y) - (R.x + R.y);
             warp_sum2(zr, zi, lane);
+            const float ay = ysc[2 * j], ray = ysc[2 * j + 1];
+            const float sxy = ax * ay;  // z = x^H y = ax ay (x~^H y~)
+            zr *= sxy;
+            zi *= sxy;
             const float bn = nrm[j];
             const float zz = zr * zr + zi * zi;
             float rel2 = 0.f;
             if (a > 0.f && bn > 0.f) rel2 = __fdividef(zz, a * bn);
             mymax = fmaxf(mymax, rel2);
             if (rel2 > tol2_rot && zz > 0.f) {
-                float c, wr, wi, taz;
-                rotation_params(a, bn, zr, zi, zz, c, wr, wi, taz);
-                const float2 cc = make_float2(c, c), pwr = make_float2(wr, wr), nwr = make_float2(-wr, -wr),
-                             pwi = make_float2(wi, wi), nwi = make_float2(-wi, -wi);
+                float c, invc, tr, ti, taz;
+                rotation_params_fast(a, bn, zr, zi, zz, c, invc, tr, ti, taz);
+                const float rho = ay * rax, sig = ax * ray;  // ay / ax , ax / ay
+                // x~' = x~ - kappa y~ , kappa = conj(tau) rho ;  y~' = y~ + lam x~ , lam = tau sig
+                const float2 nkr = make_float2(-tr * rho, -tr * rho), pki = make_float2(ti * rho, ti * rho),
+                             nki = make_float2(-ti * rho, -ti * rho);
+                const float2 plr = make_float2(tr * sig, tr * sig), pli = make_float2(ti * sig, ti * sig),
+                             nli = make_float2(-ti * sig, -ti * sig);
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    // x' = c x - conj(w) y ; y' = w x + c y
-                    const float2 vr = KEEP_Y ? yr[p] : *reinterpret_cast<const float2*>(yrp + 64 * p);
-                    const float2 vi = KEEP_Y ? yi[p] : *reinterpret_cast<const float2*>(yip + 64 * p);
-                    const float2 nxr = __ffma2_rn(cc, xr[p], __ffma2_rn(nwr, vr, __fmul2_rn(nwi, vi)));
-                    const float2 nxi = __ffma2_rn(cc, xi[p], __ffma2_rn(nwr, vi, __fmul2_rn(pwi, vr)));
-                    const float2 nyr = __ffma2_rn(cc, vr, __ffma2_rn(pwr, xr[p], __fmul2_rn(nwi, xi[p])));
-                    const float2 nyi = __ffma2_rn(cc, vi, __ffma2_rn(pwr, xi[p], __fmul2_rn(pwi, xr[p])));
-                    xr[p] = nxr;
-                    xi[p] = nxi;
-                    *reinterpret_cast<float2*>(yrp + 64 * p) = nyr;
-                    *reinterpret_cast<float2*>(yip + 64 * p) = nyi;
+                    const float2 oxr = xr[p], oxi = xi[p], oyr = yr[p], oyi = yi[p];
+                    // (kappa y)_r = rho (tr yr + ti yi) ; (kappa y)_i = rho (tr yi - ti yr)
+                    xr[p] = __ffma2_rn(nkr, oyr, __ffma2_rn(nki, oyi, oxr));
+                    xi[p] = __ffma2_rn(nkr, oyi, __ffma2_rn(pki, oyr, oxi));
+                    // (lam x)_r = sig (tr xr - ti xi) ; (lam x)_i = sig (tr xi + ti xr)
+                    *reinterpret_cast<float2*>(yrp + 64 * p) = __ffma2_rn(plr, oxr, __ffma2_rn(nli, oxi, oyr));
+                    *reinterpret_cast<float2*>(yip + 64 * p) = __ffma2_rn(plr, oxi, __ffma2_rn(pli, oxr, oyi));
                 }
+                ax *= c;
+                rax *= invc;
                 a = fmaxf(a - taz, 0.f);
-                if (lane == 0) nrm[j] = fmaxf(bn + taz, 0.f);
+                if (lane == 0) {
+                    nrm[j] = fmaxf(bn + taz, 0.f);
+                    ysc[2 * j] = ay * c;
+                    ysc[2 * j + 1] = ray * invc;
+                }
             }
         }
         __syncthreads();
@@ -355,8 +386,8 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const int t = 2 * lane + 64 * p;
-            if (t < r) Wb[(size_t)gx * ld + t] = make_float2(xr[p].x, xi[p].x);
-            if (t + 1 < r) Wb[(size_t)gx * ld + t + 1] = make_float2(xr[p].y, xi[p].y);
+            if (t < r) Wb[(size_t)gx * ld + t] = make_float2(ax * xr[p].x, ax * xi[p].x);
+            if (t + 1 < r) Wb[(size_t)gx * ld + t + 1] = make_float2(ax * xr[p].y, ax * xi[p].y);
         }
     }
     {
@@ -367,8 +398,9 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
                 const int t = 2 * lane + 64 * p;
                 const float2 vr = *reinterpret_cast<const float2*>(YR + (size_t)warp * L + t);
                 const float2 vi = *reinterpret_cast<const float2*>(YI + (size_t)warp * L + t);
-                if (t < r) Wb[(size_t)gy * ld + t] = make_float2(vr.x, vi.x);
-                if (t + 1 < r) Wb[(size_t)gy * ld + t + 1] = make_float2(vr.y, vi.y);
+                const float ay = ysc[2 * warp];
+                if (t < r) Wb[(size_t)gy * ld + t] = make_float2(ay * vr.x, ay * vi.x);
+                if (t + 1 < r) Wb[(size_t)gy * ld + t + 1] = make_float2(ay * vr.y, ay * vi.y);
             }
         }
     }
@@ -379,7 +411,7 @@ jacobi_cross_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int r, in
 template <int EPL>
 int launch_cross(vk_context* h, cudaStream_t st, float2* W, size_t mat_stride, const JacobiPlan& p, int round,
                  unsigned nblocks, float tol2_rot, unsigned* offmax, const int32_t* done) {
-    const size_t smem = (size_t)p.bsz * 32 * EPL * sizeof(float2) + (size_t)p.bsz * 8;
+    const size_t smem = (size_t)p.bsz * 32 * EPL * sizeof(float2) + (size_t)p.bsz * 16;
     if (smem > 48 * 1024)  // per-device attribute; cheap enough to set on every launch
         VK_CUDA(h, cudaFuncSetAttribute(jacobi_cross_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     jacobi_cross_kernel<EPL><<<nblocks, 32 * p.bsz, smem, st>>>(W, mat_stride, p.ld, p.r, p.bsz, p.nb, round,
