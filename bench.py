@@ -335,7 +335,11 @@ def run_ours(args):
     dom_ms = jac_ms / nlaunch if jac_ms > 0 else 0.0
     dominant = {"bound": "hbm", "kernel": "jacobi (one-sided cyclic Jacobi rotations, fp32 SIMT)",
                 "achieved": (jbytes / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": (jbytes / (dom_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if dom_ms > 0 else None, "traffic": None,
+                "frac": (jbytes / (dom_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if dom_ms > 0 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+                # (r01_ncu_full_jacobi_cross_*.txt): below the algorithmic bytes because the vectors stay L2-resident
+                "traffic": {"kat7": 65.6e6, "meerkat": None}.get(args.workload),
+                "traffic_source": "profiles/r01_ncu_full_jacobi_cross_kat7.txt" if args.workload == "kat7" else None,
                 "avg_launch_ms": dom_ms, "launches_per_step": nlaunch, "share_of_step": jac_ms / ms_per_step if ms_per_step else None,
                 "modelled_gflop_per_step": 22.0 * r ** 3 * sweeps * B / 1e9 if not eng.uses_small_path(m, n) else None,
                 "note": "latency/issue-bound fp32 rotations on L2-resident data; no HBM or tensor roofline applies, frac is informational",
@@ -383,7 +387,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="kat7", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
