@@ -288,6 +288,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->gemm_impl = (int)v;
     else if (k == "recon_generic")
         h->recon_generic = (int)v;
+    else if (k == "small_reg")
+        h->small_reg = (int)v;
     else if (k == "jacobi_generic")
         h->jacobi_generic = (int)v;
     else if (k == "chunk")

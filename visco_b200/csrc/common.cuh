@@ -40,6 +40,7 @@ struct vk_context {
     int topk = 0;            // 0 = auto (subspace iteration for compressionrank <= 4), 1 = full Jacobi only, 2 = up to rank 8
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
+    int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -588,6 +588,198 @@ int launch_small(vk_context* h, float2* W, int B, const JacobiPlan& p, float tol
     return VK_OK;
 }
 
+// Register-resident variant of the small kernel for power-of-two slot counts. A sweep is a RECURSIVE block tournament:
+// stage h = nslots/2, nslots/4, ..., 1 pairs the two halves of every block of 2h vectors. Within a stage group g keeps
+// x = vector (blk*2h + pos) in registers and meets the h vectors of the other half one per round, (pos + q) mod h, read
+// from and written back to shared memory. 32 + 16 + ... + 1 = nslots - 1 rounds per sweep as before, every group busy in
+// every round, but only y moves through shared memory: ~2.2 KB per pair instead of 5 KB (x read twice + written, y read
+// twice + written) in jacobi_small_kernel, which was bound by exactly that traffic.
+template <int LPP, int NPL>
+__global__ void __launch_bounds__(512)
+jacobi_small_reg_kernel(float2* __restrict__ W, size_t mat_stride, int ld, int ldot, int ltot, int r, int nslots, int lpad,
+                        int max_sweeps, float tol2_rot, float tol2_stop, int32_t* __restrict__ done,
+                        int32_t* __restrict__ sweeps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* XR = reinterpret_cast<float*>(smem_raw);      // [nslots][lpad]
+    float* XI = XR + (size_t)nslots * lpad;               // [nslots][lpad]
+    float* nrm = XI + (size_t)nslots * lpad;              // [nslots]
+    __shared__ unsigned cta_max;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane % LPP;
+    const int grp = (threadIdx.x / LPP);                  // group index, nslots / 2 groups in the CTA
+    float2* Wb = W + (size_t)b * mat_stride;
+
+    for (int v = warp; v < nslots; v += nwarps) {
+        float s = 0.f;
+        for (int t = lane; t < lpad; t += 32) {
+            float2 w = make_float2(0.f, 0.f);
+            if (v < r && t < ltot) w = Wb[(size_t)v * ld + t];
+            XR[(size_t)v * lpad + t] = w.x;
+            XI[(size_t)v * lpad + t] = w.y;
+            if (t < ldot) s = fmaf(w.x, w.x, fmaf(w.y, w.y, s));
+        }
+        s = warp_sum(s);
+        if (lane == 0) nrm[v] = s;
+    }
+    if (threadIdx.x == 0) cta_max = 0u;
+    __syncthreads();
+
+    int it = 0;
+    bool converged = false;
+    for (; it < max_sweeps; ++it) {
+        float mymax = 0.f;
+        for (int h = nslots >> 1; h >= 1; h >>= 1) {
+            const int blk = grp / h, pos = grp - blk * h;
+            const int xs = blk * 2 * h + pos;
+            float2 xr[NPL], xi[NPL];
+            {
+                const float* pr = XR + (size_t)xs * lpad + 2 * g;
+                const float* pi = XI + (size_t)xs * lpad + 2 * g;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    xr[p] = *reinterpret_cast<const float2*>(pr + 2 * LPP * p);
+                    xi[p] = *reinterpret_cast<const float2*>(pi + 2 * LPP * p);
+                }
+            }
+            float an = nrm[xs];
+            for (int q = 0; q < h; ++q) {
+                int yo = pos + q;
+                if (yo >= h) yo -= h;
+                const int ys = blk * 2 * h + h + yo;
+                float* yrp = XR + (size_t)ys * lpad + 2 * g;
+                float* yip = XI + (size_t)ys * lpad + 2 * g;
+                float2 yr[NPL], yi[NPL];
+                float2 P = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f), R = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    yr[p] = *reinterpret_cast<const float2*>(yrp + 2 * LPP * p);
+                    yi[p] = *reinterpret_cast<const float2*>(yip + 2 * LPP * p);
+                    const int e = 2 * g + 2 * LPP * p;
+                    if (e < ldot) {  // entries beyond ldot carry the accumulated rotations, not the vectors
+                        float2 a_r = xr[p], a_i = xi[p];
+                        if (e + 1 >= ldot) {
+                            a_r.y = 0.f;
+                            a_i.y = 0.f;
+                        }
+                        P = __ffma2_rn(a_r, yr[p], P);
+                        P = __ffma2_rn(a_i, yi[p], P);
+                        Q = __ffma2_rn(a_r, yi[p], Q);
+                        R = __ffma2_rn(a_i, yr[p], R);
+                    }
+                }
+                float zr = P.x + P.y, zi = (Q.x + Q.y) - (R.x + R.y);
+#pragma unroll
+                for (int o = LPP / 2; o > 0; o >>= 1) {
+                    zr += __shfl_xor_sync(0xffffffffu, zr, o);
+                    zi += __shfl_xor_sync(0xffffffffu, zi, o);
+                }
+                const float bn = nrm[ys];
+                const float zz = zr * zr + zi * zi;
+                float rel2 = 0.f;
+                if (an > 0.f && bn > 0.f) rel2 = __fdividef(zz, an * bn);
+                mymax = fmaxf(mymax, rel2);
+                if (rel2 > tol2_rot && zz > 0.f) {
+                    float c, wr, wi, taz;
+                    rotation_params(an, bn, zr, zi, zz, c, wr, wi, taz);
+                    const float2 cc = make_float2(c, c), pwr = make_float2(wr, wr), nwr = make_float2(-wr, -wr),
+                                 pwi = make_float2(wi, wi), nwi = make_float2(-wi, -wi);
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) {
+                        const float2 oxr = xr[p], oxi = xi[p];
+                        xr[p] = __ffma2_rn(cc, oxr, __ffma2_rn(nwr, yr[p], __fmul2_rn(nwi, yi[p])));
+                        xi[p] = __ffma2_rn(cc, oxi, __ffma2_rn(nwr, yi[p], __fmul2_rn(pwi, yr[p])));
+                        *reinterpret_cast<float2*>(yrp + 2 * LPP * p) = __ffma2_rn(cc, yr[p], __ffma2_rn(pwr, oxr, __fmul2_rn(nwi, oxi)));
+                        *reinterpret_cast<float2*>(yip + 2 * LPP * p) = __ffma2_rn(cc, yi[p], __ffma2_rn(pwr, oxi, __fmul2_rn(pwi, oxr)));
+                    }
+                    an = fmaxf(an - taz, 0.f);
+                    if (g == 0) nrm[ys] = fmaxf(bn + taz, 0.f);
+                }
+                __syncthreads();
+            }
+            {
+                float* pr = XR + (size_t)xs * lpad + 2 * g;
+                float* pi = XI + (size_t)xs * lpad + 2 * g;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    *reinterpret_cast<float2*>(pr + 2 * LPP * p) = xr[p];
+                    *reinterpret_cast<float2*>(pi + 2 * LPP * p) = xi[p];
+                }
+                if (g == 0) nrm[xs] = an;
+            }
+            __syncthreads();
+        }
+        mymax = warp_max(mymax);
+        if (lane == 0) atomicMax(&cta_max, __float_as_uint(mymax));
+        __syncthreads();
+        const float sweep_max = __uint_as_float(cta_max);
+        __syncthreads();
+        if (threadIdx.x == 0) cta_max = 0u;
+        for (int v = warp; v < r; v += nwarps) {  // refresh the cached norms from the data once per sweep
+            float s = 0.f;
+            for (int t = lane; t < ldot; t += 32) {
+                const float a_ = XR[(size_t)v * lpad + t], b_ = XI[(size_t)v * lpad + t];
+                s = fmaf(a_, a_, fmaf(b_, b_, s));
+            }
+            s = warp_sum(s);
+            if (lane == 0) nrm[v] = s;
+        }
+        __syncthreads();
+        if (sweep_max <= tol2_stop) {
+            converged = true;
+            ++it;
+            break;
+        }
+    }
+    for (int v = warp; v < r; v += nwarps)
+        for (int t = lane; t < ltot; t += 32)
+            Wb[(size_t)v * ld + t] = make_float2(XR[(size_t)v * lpad + t], XI[(size_t)v * lpad + t]);
+    if (threadIdx.x == 0) {
+        sweeps[b] = it;
+        done[b] = converged ? 1 : 0;
+    }
+}
+
+template <int LPP, int NPL>
+int launch_small_reg(vk_context* h, float2* W, int B, const JacobiPlan& p, int nslots, float tol2_rot, float tol2_stop,
+                     int32_t* done, int32_t* sweeps) {
+    const int lpad = 2 * LPP * NPL + 8;  // every lane's NPL element pairs exist (zero padded); +8 floats spreads banks
+    const int threads = (nslots / 2) * LPP;
+    const size_t smem = (size_t)nslots * lpad * 8 + (size_t)nslots * 4;
+    VK_CUDA(h, cudaFuncSetAttribute(jacobi_small_reg_kernel<LPP, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_small_reg_kernel<LPP, NPL><<<B, threads, smem, h->stream>>>(W, (size_t)p.r * p.ld, p.ld, p.ldot, p.ltot, p.r, nslots,
+                                                                       lpad, h->max_sweeps, tol2_rot, tol2_stop, done, sweeps);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+// picks (lanes per pair, element pairs per lane) for the register kernel; returns false when it does not apply
+bool small_reg_dispatch(vk_context* h, float2* W, int B, const JacobiPlan& p, float tol2_rot, float tol2_stop, int32_t* done,
+                        int32_t* sweeps, int* rc) {
+    int nslots = 2;
+    while (nslots < p.r) nslots <<= 1;
+    if (2 * nslots > 3 * (p.r + (p.r & 1))) return false;  // too many phantom vectors: the plain tournament is cheaper
+    const int L = p.ltot;
+    int lpp, npl;
+    if (L <= 32) lpp = 4, npl = 4;
+    else if (L <= 64) lpp = 4, npl = 8;
+    else if (L <= 128) lpp = 8, npl = 8;
+    else if (L <= 256) lpp = 16, npl = 8;
+    else if (L <= 512) lpp = 32, npl = 8;
+    else return false;
+    const int threads = (nslots / 2) * lpp;
+    if (threads > 512 || threads < 32) return false;
+    if ((size_t)nslots * (2 * lpp * npl + 8) * 8 + 1024 > 220 * 1024) return false;
+#define VK_SMALL_REG(LP, NP) *rc = launch_small_reg<LP, NP>(h, W, B, p, nslots, tol2_rot, tol2_stop, done, sweeps)
+    if (lpp == 4 && npl == 4) VK_SMALL_REG(4, 4);
+    else if (lpp == 4) VK_SMALL_REG(4, 8);
+    else if (lpp == 8) VK_SMALL_REG(8, 8);
+    else if (lpp == 16) VK_SMALL_REG(16, 8);
+    else VK_SMALL_REG(32, 8);
+#undef VK_SMALL_REG
+    return true;
+}
+
 __global__ void sweep_check_kernel(int B, float tol2_stop, unsigned* __restrict__ offmax, int32_t* __restrict__ done,
                                    int32_t* __restrict__ sweeps, int32_t* __restrict__ active) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -666,6 +858,8 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
     const long long nblocks = (long long)B * (p.nb / 2);
     if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "jacobi: batch too large");
     if (p.nb == 2 && !h->jacobi_generic) {
+        int rc_small = VK_OK;
+        if (h->small_reg && small_reg_dispatch(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev, &rc_small)) return rc_small;
         // elements per lane ~ 8..16: lanes per pair from the vector length
         const int want = (p.ltot + 15) / 16;
         if (want <= 4) return launch_small<4>(h, W, B, p, tol2_rot, tol2_stop, done_dev, sweeps_dev);
