@@ -60,7 +60,9 @@ int vk_sync(vk_handle h);
  *          "check_finite" (default 1), "check_every" (host convergence poll period in sweeps, default 1),
  *          "jacobi_bsz" (vectors per block, 0 = auto), "jacobi_groups" (concurrent matrix groups, 0 = auto), "chunk" (matrices per internal pass, 0 = auto),
  *          "stage_timing" (0/1, see vk_last_stage_ms), "topk" (0 = blocked subspace iteration for fixed rank <= 4 with
- *          fallback to the full solver, 1 = full solver only, 2 = also for ranks up to 8), "gemm_impl" (0 = tcgen05 GEMM for k > 8, 1 = SIMT). */
+ *          fallback to the full solver, 1 = full solver only, 2 = also for ranks up to 8), "gemm_impl" (0 = tcgen05 GEMM for k > 8, 1 = SIMT),
+ *          "small_reg" (1 = register-resident recursive-tournament kernel on the small path where the shape allows
+ *          (default), 0 = shared-memory round-robin kernel only). */
 int vk_set_option(vk_handle h, const char* key, double value);
 /* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own
  * workspace when ws == NULL). */
