@@ -156,20 +156,29 @@ def test_gram_stage_tcgen05(eng, torch):
     assert not eng.gram_uses_tcgen05(64, 4096) and not eng.gram_uses_tcgen05(300, 200)
 
 
-def test_eigh_stage(eng, torch):
-    m, n = 160, 400
+@pytest.mark.parametrize("impl,m,n", [(1, 160, 400), (2, 160, 400), (2, 65, 97), (2, 100, 64), (2, 333, 700),
+                                      (2, 2, 5), (2, 3, 9), (2, 600, 1200)])
+def test_eigh_stage(eng, torch, impl, m, n):
+    """vk_eigh_jacobi_batched with the cyclic Jacobi solver (eig_impl=1) and the direct one (eig_impl=2:
+    tridiagonalisation + implicit QL): eigenvalues, orthonormality of the vectors, residuals of the leading pairs."""
     A = _device_cube(eng, torch, 2, 2, m, n)
     W = eng.gram(A, impl=1)
+    r = W.shape[1]
     G = W.cpu().numpy().astype(np.complex128).transpose(0, 2, 1)
-    lam, info = eng.eigh_jacobi(W)
+    eng.set_option("eig_impl", impl)
+    try:
+        lam, info = eng.eigh_jacobi(W)
+    finally:
+        eng.set_option("eig_impl", 0)
     lam, info, Wn = lam.cpu().numpy(), info.cpu().numpy(), W.cpu().numpy().astype(np.complex128)
-    assert np.all(info[:, 1] == 1) and np.all(info[:, 0] <= 20)
+    # info[:, 0]: Jacobi sweeps, or QL iterations (LAPACK's bound is 30 per eigenvalue)
+    assert np.all(info[:, 1] == 1) and np.all(info[:, 0] <= (20 if impl == 1 else 30 * r))
     for b in range(G.shape[0]):
         ev = np.linalg.eigvalsh(G[b])[::-1]
         np.testing.assert_allclose(lam[b], ev, atol=3e-6 * ev[0])
         V = Wn[b] / np.linalg.norm(Wn[b], axis=1, keepdims=True)        # rows = eigenvectors
-        assert np.abs(V.conj() @ V.T - np.eye(m)).max() < 1e-4
-        top = np.argsort(-np.linalg.norm(Wn[b], axis=1))[:10]
+        assert np.abs(V.conj() @ V.T - np.eye(r)).max() < 1e-4
+        top = np.argsort(-np.linalg.norm(Wn[b], axis=1))[:min(10, r)]
         for i in top:
             v = V[i]
             rq = np.real(v.conj() @ G[b] @ v)
@@ -387,19 +396,29 @@ def test_handles_are_independent_and_thread_safe(torch):
 
 
 def test_internal_scheduling_options_do_not_change_results(eng, torch):
-    """chunking, stream groups and the generic Jacobi kernels are performance knobs only."""
+    """chunking, stream groups, the generic Jacobi kernels and the choice of eigensolver are performance knobs only."""
     A = _device_cube(eng, torch, 3, 4, 192, 384)
-    base = eng.compress(A, decorrelation=0.97)
+    keys = ("chunk", "jacobi_groups", "jacobi_generic", "gram_impl", "gemm_impl", "eig_impl")
     try:
-        for opts in ({"chunk": 5}, {"jacobi_groups": 1}, {"jacobi_groups": 4}, {"jacobi_generic": 1}, {"gram_impl": 1},
-                     {"gemm_impl": 1}):
-            for k_, v_ in opts.items():
-                eng.set_option(k_, v_)
-            got = eng.compress(A, decorrelation=0.97)
-            for k_ in opts:
-                eng.set_option(k_, 0)
-            assert torch.equal(got[3], base[3]), opts
-            assert float(((got[1] - base[1]).abs() / base[1].clamp_min(1e-20)).max()) < 2e-5, opts
+        for eig in (1, 2):
+            eng.set_option("eig_impl", eig)
+            base = eng.compress(A, decorrelation=0.97)
+            if eig == 1:
+                jacobi = base
+            variants = ({"chunk": 5}, {"gram_impl": 1}, {"gemm_impl": 1})
+            if eig == 1:
+                variants += ({"jacobi_groups": 1}, {"jacobi_groups": 4}, {"jacobi_generic": 1})
+            for opts in variants:
+                for k_, v_ in opts.items():
+                    eng.set_option(k_, v_)
+                got = eng.compress(A, decorrelation=0.97)
+                for k_ in opts:
+                    eng.set_option(k_, 0)
+                assert torch.equal(got[3], base[3]), (eig, opts)
+                assert float(((got[1] - base[1]).abs() / base[1].clamp_min(1e-20)).max()) < 2e-5, (eig, opts)
+        # the two eigensolvers against each other: same ranks, same singular values
+        assert torch.equal(base[3], jacobi[3])
+        assert float(((base[1] - jacobi[1]).abs() / jacobi[1].clamp_min(1e-20)).max()) < 1e-4
     finally:
-        for k_ in ("chunk", "jacobi_groups", "jacobi_generic", "gram_impl", "gemm_impl"):
+        for k_ in keys:
             eng.set_option(k_, 0)

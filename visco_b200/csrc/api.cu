@@ -9,7 +9,7 @@ namespace {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-    size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, xbuf, total;
+    size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, xbuf, eig, total;
 };
 
 bool small_path(int m, int n) {
@@ -19,7 +19,16 @@ bool small_path(int m, int n) {
     return (size_t)(r + (r & 1)) * (size_t)(L + r) * sizeof(float2) + 1024 <= VK_SMEM_BUDGET;
 }
 
-WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0) {
+// eigensolver of the Gram path: 2 = tridiagonalisation + implicit QL, 1 = cyclic Jacobi, 0 = auto (QL where it is
+// supported, except for fixed ranks the blocked subspace iteration handles)
+bool use_qr(const vk_context* h, int m, int n, int fixed_rank = 0) {
+    const int r = m < n ? m : n;
+    if (!h || small_path(m, n) || !vk_eigqr_supported(r) || h->eig_impl == 1) return false;
+    if (h->eig_impl == 2) return true;
+    return !(h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2));
+}
+
+WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false) {
     if (gchunk < chunk) gchunk = chunk;
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
@@ -40,14 +49,25 @@ WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0) {
     // K-major copy of conj(U_k)^T for the tcgen05 V-formation (wide Gram path, k > 8)
     w.xbuf = off;
     if (!small_path(m, n) && m <= n && vk_cgemm_tc_supported(m, n, kmax)) off += align_up((size_t)chunk * kmax * m * 8);
+    w.eig = off;
+    if (qr) off += align_up(vk_eigqr_scratch_bytes(chunk, r));
     w.total = off;
     return w;
 }
 
-int auto_chunk(const vk_context* h, int B, int m, int n) {
-    (void)h;
+int auto_chunk(const vk_context* h, int B, int m, int n, bool qr) {
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
+    if (qr) {
+        // the direct solver runs one CTA per matrix in its first stage: two waves of matrices per pass, bounded by
+        // 8 GB of rotation scratch
+        size_t c = 2 * (size_t)(h ? h->num_sms : 148);
+        const size_t per = vk_eigqr_scratch_bytes(1, r);
+        if (c * per > ((size_t)8 << 30)) c = ((size_t)8 << 30) / per;
+        if (c < 1) c = 1;
+        if (c > (size_t)B) c = B;
+        return (int)c;
+    }
     const size_t per = small_path(m, n) ? (size_t)r * (L + r) * 8 : (size_t)r * r * 8;
     // keep the Jacobi working set of one internal pass inside ~half of the 126 MB L2, but never below a few waves
     size_t c = (64u << 20) / (per ? per : 1);
@@ -157,9 +177,13 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         if (!gram_done && (rc = gram_stage(h, A, B, m, n, W, gscale, nonfinite))) return rc;
         tm.mark(1);
         // fixed small rank: blocked subspace iteration first; the full Jacobi solver only sees what it left unsolved
-        const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
-        if (fast && (rc = vk_launch_topk(h, W, B, r, fixed_rank, done, sweeps))) return rc;
-        if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active, fast))) return rc;
+        if (use_qr(h, m, n, fixed_rank)) {
+            if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done))) return rc;
+        } else {
+            const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
+            if (fast && (rc = vk_launch_topk(h, W, B, r, fixed_rank, done, sweeps))) return rc;
+            if ((rc = vk_launch_jacobi(h, W, B, p, sweeps, done, offmax, active, fast))) return rc;
+        }
         tm.mark(2);
         if ((rc = vk_launch_select(h, W, B, r, p.ldot, p.ld, gscale, 1, fixed_rank, decorrelation, kmax, perm, inv, S,
                                    ranks, stats, sweeps, done)))
@@ -292,6 +316,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->small_reg = (int)v;
     else if (k == "jacobi_generic")
         h->jacobi_generic = (int)v;
+    else if (k == "eig_impl")
+        h->eig_impl = (int)v;
     else if (k == "chunk")
         h->chunk = (int)v;
     else
@@ -301,9 +327,17 @@ int vk_set_option(vk_handle h, const char* key, double v) {
 
 size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax) {
     if (B <= 0 || m < 1 || n < 1 || kmax < 1) return 0;
-    int chunk = (h && h->chunk > 0) ? h->chunk : auto_chunk(h, B, m, n);
-    if (chunk > B) chunk = B;
-    return ws_layout(chunk, m, n, kmax, gram_chunk(B, chunk, m, n)).total;
+    // the rank rule is not known here: report the larger of the two eigensolver configurations
+    size_t need = 0;
+    for (int q = 0; q < 2; ++q) {
+        const bool qr = q == 1;
+        if (qr && !use_qr(h, m, n, 0)) continue;
+        int chunk = (h && h->chunk > 0) ? h->chunk : auto_chunk(h, B, m, n, qr);
+        if (chunk > B) chunk = B;
+        const size_t t = ws_layout(chunk, m, n, kmax, gram_chunk(B, chunk, m, n), qr).total;
+        if (t > need) need = t;
+    }
+    return need;
 }
 
 int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(m, n)) ? 1 : 0; }
@@ -322,10 +356,11 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     if (decorrelation < 0.0 || !(decorrelation == decorrelation))
         return vk_fail(h, VK_EINVAL, "decorrelation must be >= 0");
     VK_CUDA(h, cudaSetDevice(h->device));
-    int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n);
+    const bool qr = use_qr(h, m, n, fixed_rank);
+    int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n, qr);
     if (chunk > B) chunk = B;
     const int gchunk = gram_chunk(B, chunk, m, n);
-    const WsLayout L = ws_layout(chunk, m, n, kmax, gchunk);
+    const WsLayout L = ws_layout(chunk, m, n, kmax, gchunk, qr);
     unsigned char* wsp = static_cast<unsigned char*>(ws);
     if (!wsp) {
         if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total))) return rc;
@@ -530,6 +565,9 @@ int vk_eigh_jacobi_batched(vk_handle h, void* W, int B, int r, float* lambda, in
     const size_t o_st = off; off += align_up((size_t)B * 16);
     const size_t o_ac = off; off += 256;
     const size_t o_nf = off; off += 256;
+    const bool qr = h->eig_impl != 1 && vk_eigqr_supported(r);
+    const size_t o_eig = off;
+    if (qr) off += align_up(vk_eigqr_scratch_bytes(B, r));
     if ((rc = ensure(h, &h->ws, &h->ws_bytes, off))) return rc;
     unsigned char* ws = static_cast<unsigned char*>(h->ws);
     int32_t* perm = reinterpret_cast<int32_t*>(ws + o_perm);
@@ -545,8 +583,12 @@ int vk_eigh_jacobi_batched(vk_handle h, void* W, int B, int r, float* lambda, in
     float2* Wp = static_cast<float2*>(W);
     VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
     if ((rc = vk_launch_gram_normalise(h, Wp, B, r, gscale, nonfinite))) return rc;
-    const JacobiPlan p = vk_jacobi_plan(h, r, r, r);
-    if ((rc = vk_launch_jacobi(h, Wp, B, p, sweeps, done, offmax, active))) return rc;
+    if (qr) {
+        if ((rc = vk_launch_eigqr(h, Wp, B, r, r, ws + o_eig, sweeps, done))) return rc;
+    } else {
+        const JacobiPlan p = vk_jacobi_plan(h, r, r, r);
+        if ((rc = vk_launch_jacobi(h, Wp, B, p, sweeps, done, offmax, active))) return rc;
+    }
     // mode 2: report the eigenvalues themselves (norm * trace scale), sorted descending
     if ((rc = vk_launch_select(h, Wp, B, r, r, r, gscale, 2, 0, 0.f, r, perm, inv, lambda, ranks, stats, sweeps, done)))
         return rc;

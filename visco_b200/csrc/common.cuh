@@ -42,6 +42,7 @@ struct vk_context {
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
+    int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -103,6 +104,11 @@ JacobiPlan vk_jacobi_plan(const vk_context* h, int r, int ldot, int ltot);
 // preset_done: done_dev / sweeps_dev already hold the verdict of the fixed-rank fast path (1 = solved, skip)
 int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32_t* sweeps_dev, int32_t* done_dev,
                      unsigned* offmax_dev, int32_t* active_dev, bool preset_done = false);
+// direct eigensolver (tridiag.cu): same W in/out contract as vk_launch_jacobi for the Gram path (ldot = ltot = r)
+bool vk_eigqr_supported(int r);
+size_t vk_eigqr_scratch_bytes(int B, int r);
+int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
+                    int32_t* done_dev);
 bool vk_topk_supported(int r, int fixed_rank, bool force);
 int vk_launch_topk(vk_context* h, float2* W, int B, int r, int fixed_rank, int32_t* done_dev, int32_t* sweeps_dev);
 

@@ -1,0 +1,729 @@
+// Hermitian eigensolver, direct variant ("eig_impl" = 2): Householder tridiagonalisation -> implicit QL on the real
+// tridiagonal with every plane rotation recorded and level-scheduled -> rotations applied to the accumulated
+// reflectors. About 10x fewer flops than nine cyclic Jacobi sweeps; float32 throughout (prototype with the measured
+// accuracy: tools/proto_tridiag.py). Replaces the LAPACK cgesdd call behind np.linalg.svd (reference compress_ms.py:
+// apply_svd) together with the Gram product and the factor formation; parity is checked through the same tests as the
+// Jacobi solver.
+//
+// Conventions: M = W[b] is the r x r row-major Hermitian matrix conj(G) (row i of W = column i of the Gram matrix G).
+//   M = Q T Q^H,  Q = H_0 H_1 ... H_{r-3},  H_j = I - tau_j v_j v_j^H   (v_j lives on indices j+1 .. r-1)
+//   T = D T_real D^H with unit phases D, T_real = Z Lambda Z^T  =>  eigenvectors of M are the columns of Q D Z.
+// Xt holds (Q D Z)^T: row i is eigenvector i, so a plane rotation of columns (i, i+1) of Z acts on rows i, i+1 of Xt.
+// On exit W[b][i][:] = lambda_i * conj(Xt[i][:]) - the layout the Jacobi solver leaves (vectors of norm lambda_i).
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TD_THREADS = 512;
+constexpr int TD_WARPS = TD_THREADS / 32;
+constexpr int FQ_THREADS = 256;
+constexpr int FQ_WARPS = FQ_THREADS / 32;
+constexpr int FQ_TJ = 8;  // reflectors staged per shared-memory tile
+constexpr int RA_C = 8;     // columns of Xt per slab = lanes per application slot
+constexpr int RA_NS = 64;   // application slots per CTA = sweeps in flight
+constexpr int RA_THREADS = RA_C * RA_NS;
+constexpr int QL_MAXIT = 60;
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// block-wide sum of a float2 (TD_THREADS threads), result to every thread; two barriers, the first of which also
+// publishes whatever the callers wrote to shared memory before the call
+__device__ __forceinline__ float2 block_sum2(float2 v, float2* scratch) {
+    v.x = warp_sum(v.x);
+    v.y = warp_sum(v.y);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float2 t = lane < TD_WARPS ? scratch[lane] : make_float2(0.f, 0.f);
+    t.x = warp_sum(t.x);
+    t.y = warp_sum(t.y);
+    return t;
+}
+
+// ---- 1. tridiagonalisation: one CTA per matrix, matrix in global memory (L2). The two-sided rank-2 update of step
+//         j-1 is fused with the matrix-vector product of step j: one read + one write of the trailing block per step.
+//         Lane l of a warp owns the absolute columns k = 32 e + l; a warp stages RB whole rows in registers before it
+//         touches them, so RB * (r - j) / 32 loads per lane are in flight (the kernel is L2-latency bound otherwise).
+//         All shared vectors are indexed by absolute column. -------------------------------------------------------
+template <int EPL, int RB>
+__global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
+    tridiag_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
+                   float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall) {
+    constexpr int WD = EPL * 32;
+    extern __shared__ float2 td_sm[];
+    float2* vprev = td_sm;
+    float2* vnew = td_sm + WD;
+    float2* wv = td_sm + 2 * WD;
+    float2* pv = td_sm + 3 * WD;
+    float2* nrow = td_sm + 4 * WD;  // row j+1 as the pass of step j left it (saves a global round trip per step)
+    __shared__ float2 scratch[TD_WARPS];
+    __shared__ float s_tau;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* M = Wall + (size_t)b * wstride;
+    float* d = dall + (size_t)b * r;
+    float* e = eall + (size_t)b * r;
+    float* taus = tauall + (size_t)b * r;
+    float2* ph = phall + (size_t)b * r;
+    float2 phase = make_float2(1.f, 0.f);
+    if (tid == 0) ph[0] = phase;
+    for (int k = tid; k < 5 * WD; k += TD_THREADS) td_sm[k] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    for (int j = 0; j + 2 < r; ++j) {
+        const int e0 = (j + 1) >> 5;
+        // row j with the pending update of step j-1 applied: diagonal d_j and the column below it (a = conj(row))
+        float ss = 0.f;
+        {
+            const float2 v0 = vprev[j], w0 = wv[j];  // zero while j == 0
+            for (int k = tid; k < WD; k += TD_THREADS) {
+                float2 a = make_float2(0.f, 0.f);
+                if (k >= j && k < r) {
+                    float2 x = (j == 0) ? M[k] : nrow[k];
+                    const float2 wk = wv[k], vk = vprev[k];
+                    x.x -= v0.x * wk.x + v0.y * wk.y + w0.x * vk.x + w0.y * vk.y;
+                    x.y -= v0.y * wk.x - v0.x * wk.y + w0.y * vk.x - w0.x * vk.y;
+                    if (k == j) {
+                        d[j] = x.x;
+                    } else {
+                        a = make_float2(x.x, -x.y);
+                        ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                    }
+                }
+                vnew[k] = a;
+            }
+        }
+        const float2 tot = block_sum2(make_float2(ss, 0.f), scratch);
+        if (tid == 0) {
+            float tau = 0.f, ej = 0.f;
+            if (tot.x > 1e-30f) {
+                const float xn = sqrtf(tot.x);
+                const float2 alpha = vnew[j + 1];
+                const float aa = sqrtf(alpha.x * alpha.x + alpha.y * alpha.y);
+                float2 p1 = make_float2(1.f, 0.f);
+                if (aa > 0.f) p1 = make_float2(alpha.x / aa, alpha.y / aa);
+                vnew[j + 1] = make_float2(alpha.x + p1.x * xn, alpha.y + p1.y * xn);
+                tau = 1.f / (xn * (xn + aa));
+                ej = xn;
+                phase = cmulf(phase, make_float2(-p1.x, -p1.y));  // sub-diagonal element is -p1 * xn
+            }
+            taus[j] = tau;
+            e[j] = ej;
+            ph[j + 1] = phase;
+            s_tau = tau;
+        }
+        __syncthreads();
+        const float tau = s_tau;
+        // the reflector replaces the (now dead) part of row j right of the diagonal
+        {
+            float2* row = M + (size_t)j * ld;
+            for (int k = j + 1 + tid; k < r; k += TD_THREADS) row[k] = vnew[k];
+        }
+        // fused pass over the trailing block
+        for (int ib = j + 1 + warp; ib < r; ib += TD_WARPS * RB) {
+            float2 x[RB][EPL];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int i = ib + q * TD_WARPS;
+                const float2* row = M + (size_t)i * ld;
+#pragma unroll
+                for (int ee = 0; ee < EPL; ++ee) {
+                    const int k = ee * 32 + lane;
+                    x[q][ee] = (ee >= e0 && k > j && k < r && i < r) ? row[k] : make_float2(0.f, 0.f);
+                }
+            }
+            float2 vi[RB], wi[RB], acc[RB];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int i = ib + q * TD_WARPS;
+                vi[q] = i < r ? vprev[i] : make_float2(0.f, 0.f);
+                wi[q] = i < r ? wv[i] : make_float2(0.f, 0.f);
+                acc[q] = make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int ee = 0; ee < EPL; ++ee) {
+                const int k = ee * 32 + lane;
+                if (ee >= e0 && k > j && k < r) {
+                    const float2 wk = wv[k], vk = vprev[k], vn = vnew[k];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        float2 t = x[q][ee];
+                        t.x -= vi[q].x * wk.x + vi[q].y * wk.y + wi[q].x * vk.x + wi[q].y * vk.y;
+                        t.y -= vi[q].y * wk.x - vi[q].x * wk.y + wi[q].y * vk.x - wi[q].x * vk.y;
+                        x[q][ee] = t;
+                        cfma(acc[q], t, vn);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+                const int i = ib + q * TD_WARPS;
+                if (i < r) {
+                    float2* row = M + (size_t)i * ld;
+                    if (j > 0) {
+#pragma unroll
+                        for (int ee = 0; ee < EPL; ++ee) {
+                            const int k = ee * 32 + lane;
+                            if (ee >= e0 && k > j && k < r) row[k] = x[q][ee];
+                        }
+                    }
+                    if (i == j + 1) {
+#pragma unroll
+                        for (int ee = 0; ee < EPL; ++ee) {
+                            const int k = ee * 32 + lane;
+                            if (ee >= e0 && k > j && k < r) nrow[k] = x[q][ee];
+                        }
+                    }
+                    const float ax = warp_sum(acc[q].x), ay = warp_sum(acc[q].y);
+                    if (lane == 0) pv[i] = make_float2(tau * ax, tau * ay);
+                }
+            }
+        }
+        __syncthreads();
+        // K = tau/2 * v^H p ;  w = p - K v
+        float2 part = make_float2(0.f, 0.f);
+        for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
+            const float2 v = vnew[k], p = pv[k];
+            part.x += v.x * p.x + v.y * p.y;
+            part.y += v.x * p.y - v.y * p.x;
+        }
+        const float2 kk = block_sum2(part, scratch);
+        const float2 K = make_float2(0.5f * tau * kk.x, 0.5f * tau * kk.y);
+        for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
+            const float2 v = vnew[k], p = pv[k];
+            wv[k] = make_float2(p.x - (K.x * v.x - K.y * v.y), p.y - (K.x * v.y + K.y * v.x));
+        }
+        float2* t = vprev;
+        vprev = vnew;
+        vnew = t;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (r == 1) {
+            d[0] = M[0].x;
+        } else {
+            const int j = r - 2;
+            float2 x00 = M[(size_t)j * ld + j], x01 = M[(size_t)j * ld + j + 1], x11 = M[(size_t)(j + 1) * ld + j + 1];
+            if (r >= 3) {
+                const float2 v0 = vprev[j], v1 = vprev[j + 1], w0 = wv[j], w1 = wv[j + 1];
+                x00.x -= 2.f * (v0.x * w0.x + v0.y * w0.y);
+                x11.x -= 2.f * (v1.x * w1.x + v1.y * w1.y);
+                x01.x -= v0.x * w1.x + v0.y * w1.y + w0.x * v1.x + w0.y * v1.y;
+                x01.y -= v0.y * w1.x - v0.x * w1.y + w0.y * v1.x - w0.x * v1.y;
+            }
+            d[j] = x00.x;
+            d[j + 1] = x11.x;
+            const float ea = sqrtf(x01.x * x01.x + x01.y * x01.y);  // sub-diagonal element is conj(x01)
+            e[j] = ea;
+            if (ea > 0.f) phase = cmulf(phase, make_float2(x01.x / ea, -x01.y / ea));
+            ph[j + 1] = phase;
+            taus[j] = 0.f;
+        }
+        e[r - 1] = 0.f;
+        taus[r - 1] = 0.f;
+    }
+}
+
+// ---- 2. Xt0 = (Q D)^T: row i = H_0 ... H_{r-3} e_i, kept in the registers of one warp for all reflectors -------------
+template <int EPL, int RPW>
+__global__ void __launch_bounds__(FQ_THREADS, (EPL <= 16) ? 2 : 1)
+    formq_kernel(const float2* __restrict__ Wall, int r, int ld, size_t wstride, const float* __restrict__ tauall,
+                 const float2* __restrict__ phall, float2* __restrict__ Xall) {
+    constexpr int WIDTH = EPL * 32;
+    extern __shared__ float2 fq_sv[];  // [FQ_TJ][WIDTH]
+    __shared__ float stau[FQ_TJ];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float2* M = Wall + (size_t)b * wstride;
+    const float* taus = tauall + (size_t)b * r;
+    const int rbase = blockIdx.x * (FQ_WARPS * RPW);
+    const int i0 = rbase + warp * RPW;
+    int imax = rbase + FQ_WARPS * RPW - 1;
+    if (imax > r - 1) imax = r - 1;
+
+    float2 y[RPW][EPL];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q)
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) y[q][e] = make_float2((e * 32 + lane == i0 + q) ? 1.f : 0.f, 0.f);
+
+    int jstart = imax - 1;
+    if (jstart > r - 3) jstart = r - 3;
+    for (int jt = jstart; jt >= 0; jt -= FQ_TJ) {
+        __syncthreads();
+        for (int idx = tid; idx < FQ_TJ * WIDTH; idx += FQ_THREADS) {
+            const int t = idx / WIDTH, k = idx - t * WIDTH, j = jt - t;
+            float2 v = make_float2(0.f, 0.f);
+            if (j >= 0 && k > j && k < r) v = M[(size_t)j * ld + k];
+            fq_sv[idx] = v;
+        }
+        if (tid < FQ_TJ) stau[tid] = (jt - tid >= 0) ? taus[jt - tid] : 0.f;
+        __syncthreads();
+#pragma unroll 1
+        for (int t = 0; t < FQ_TJ; ++t) {
+            const int j = jt - t;
+            if (j < 0) break;
+            const float tau = stau[t];
+            if (tau == 0.f || i0 + RPW - 1 <= j) continue;
+            const int e0 = (j + 1) >> 5;
+            float2 v[EPL];
+#pragma unroll
+            for (int e = 0; e < EPL; ++e)
+                if (e >= e0) v[e] = fq_sv[t * WIDTH + e * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                if (i0 + q <= j) continue;
+                float2 u = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (e >= e0) {
+                        u.x = fmaf(v[e].x, y[q][e].x, fmaf(v[e].y, y[q][e].y, u.x));
+                        u.y = fmaf(v[e].x, y[q][e].y, fmaf(-v[e].y, y[q][e].x, u.y));
+                    }
+                u.x = tau * warp_sum(u.x);
+                u.y = tau * warp_sum(u.y);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (e >= e0) {
+                        y[q][e].x = fmaf(-u.x, v[e].x, fmaf(u.y, v[e].y, y[q][e].x));
+                        y[q][e].y = fmaf(-u.x, v[e].y, fmaf(-u.y, v[e].x, y[q][e].y));
+                    }
+            }
+        }
+    }
+    float2* X = Xall + (size_t)b * r * r;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+        const int i = i0 + q;
+        if (i >= r) continue;
+        const float2 p = phall[(size_t)b * r + i];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int k = e * 32 + lane;
+            if (k < r) X[(size_t)i * r + k] = cmulf(y[q][e], p);
+        }
+    }
+}
+
+__device__ __forceinline__ float2 lds_v2(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- 3. implicit QL on the real tridiagonal, one warp per matrix: lane 0 runs the (inherently serial) chase and
+//         records each rotation. The loop is latency bound (one active lane, in-order issue), so (d_i, e_i) are
+//         interleaved and fetched with one 64-bit load one rotation ahead, the hypot-underflow test and the Newton
+//         correction of the reciprocal square root sit off the dependent chain, and nothing but the recurrence and
+//         one store of (c, s) happens per rotation.
+//         Scheduling: the rotation of sweep s on rows (i, i+1) gets level key_s - i with
+//         key_s = max(key_{s-1} + 2, top_s + 1, end level of sweep s - NS + top_s): consecutive sweeps trail each
+//         other by two rows, so the rotations of one level touch disjoint row pairs, every rotation comes after all
+//         earlier ones on its rows, and sweep s can reuse the application slot of sweep s - NS. --------------------
+struct SweepRec {
+    int q0, top, cnt, base;  // first rotation, first row i, rotations, level of the first rotation
+    float2 p[8];             // the first eight (c, s): saves the consumer a dependent load
+};
+
+__global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict__ dall, const float* __restrict__ eall,
+                                                 float* __restrict__ lamall, float2* __restrict__ csall,
+                                                 SweepRec* __restrict__ swall, int32_t* __restrict__ metaall, int cap,
+                                                 int scap, int lcap) {
+    extern __shared__ float ql_sm[];
+    float2* de = reinterpret_cast<float2*>(ql_sm) + 1;  // de[i] = (d_i, e_i), i = -1 .. r-1 (de[-1] is a pad)
+    int* endlv = reinterpret_cast<int*>(ql_sm + 2 * (r + 2));  // [RA_NS] end level of the last sweep of each slot
+    const int b = blockIdx.x, lane = threadIdx.x;
+    float2* cs = csall + (size_t)b * cap;
+    SweepRec* sw = swall + (size_t)b * scap;
+    // QL deflates from the top and needs the large entries at the bottom (LAPACK steqr picks QL or QR by the same
+    // test); the tridiagonalisation above leaves them at the top, so the iteration usually runs on the index-reversed
+    // matrix: d'[i] = d[r-1-i], e'[i] = e[r-2-i]. The consumer then loads the rows of Xt in reversed order.
+    const bool rev = r > 1 && fabsf(dall[(size_t)b * r]) > fabsf(dall[(size_t)b * r + r - 1]);
+    for (int i = lane; i < r; i += 32) {
+        const int src = rev ? r - 1 - i : i;
+        const float ee = rev ? (i < r - 1 ? eall[(size_t)b * r + r - 2 - i] : 0.f) : eall[(size_t)b * r + i];
+        de[i] = make_float2(dall[(size_t)b * r + src], ee);
+    }
+    for (int i = lane; i < RA_NS; i += 32) endlv[i] = 0;
+    if (lane == 0) de[-1] = make_float2(0.f, 0.f);
+    __syncwarp();
+    const unsigned de_sa = (unsigned)__cvta_generic_to_shared(de);
+    int nrot = 0, ns = 0, key = -1, nlev = 0, iters = 0, status = 0;
+    for (int l = 0; l < r && status == 0; ++l) {
+        int it = 0;
+        while (true) {
+            // smallest m >= l with a negligible e[m] (warp-cooperative scan)
+            int m = r - 1;
+            for (int base = l; base < r - 1; base += 32) {
+                const int idx = base + lane;
+                bool ok = false;
+                if (idx < r - 1) {
+                    const float2 a = de[idx];
+                    const float dd = fabsf(a.x) + fabsf(de[idx + 1].x);
+                    ok = (fabsf(a.y) + dd == dd);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                if (mask) {
+                    m = base + __ffs(mask) - 1;
+                    break;
+                }
+            }
+            if (m == l) break;
+            if (++it > QL_MAXIT) {
+                status = 2;
+                break;
+            }
+            ++iters;
+            int st0 = 0;
+            if (lane == 0) {
+                if (nrot + (m - l) > cap || ns >= scap) {
+                    st0 = 1;
+                } else {
+                    const float dl = de[l].x, el = de[l].y;
+                    float g = (de[l + 1].x - dl) / (2.f * el);
+                    float rr = sqrtf(fmaf(g, g, 1.f));
+                    g = de[m].x - dl + el / (g + copysignf(rr, g));
+                    float s = 1.f, c = 1.f, p = 0.f;
+                    bool early = false;
+                    int i = m - 1;
+                    const int top = i;
+                    float d_hi = de[m].x, d_lo = de[i].x, e_i = de[i].y;
+                    unsigned a = de_sa + 8u * (unsigned)i;  // shared address of de[i]
+                    float2* csp = cs + nrot;
+#pragma unroll 2
+                    for (; i >= l; --i) {
+                        const float2 nx = lds_v2(a - 8u);  // (d, e)[i-1], used by the next rotation
+                        const float f = s * e_i, bb2 = 2.f * c * e_i, ff = f * f;
+                        const float x = fmaf(g, g, ff);
+                        const float y0 = rsqrt_ftz(x);
+                        // y = y0 (1 + hh), hh = (1 - x y0^2) / 2: one Newton step, applied to the products
+                        const float hh = fmaf(-0.5f * x * y0, y0, 0.5f);
+                        const float c0 = g * y0, s0 = f * y0, r0 = x * y0;
+                        const float cn = fmaf(c0, hh, c0), sn = fmaf(s0, hh, s0);
+                        const float g1 = d_hi - p;
+                        rr = fmaf(d_lo - g1, sn, cn * bb2);
+                        const float pn = sn * rr;
+                        if (x < 1e-36f) {  // hypot underflow: the reference algorithm's r == 0 recovery
+                            sts_f32(a + 12u, 0.f);
+                            sts_f32(a + 8u, d_hi - p);
+                            de[m].y = 0.f;
+                            early = true;
+                            break;
+                        }
+                        sts_f32(a + 12u, fmaf(r0, hh, r0));  // e[i+1]
+                        sts_f32(a + 8u, g1 + pn);           // d[i+1]
+                        g = fmaf(cn, rr, -0.5f * bb2);
+                        s = sn, c = cn, p = pn;
+                        *csp++ = make_float2(cn, sn);
+                        d_hi = d_lo, d_lo = nx.x, e_i = nx.y;
+                        a -= 8u;
+                    }
+                    if (!early) {
+                        de[l].x = d_hi - p;
+                        de[l].y = g;
+                        de[m].y = 0.f;
+                    }
+                    const int applied = top - i;
+                    if (applied > 0) {
+                        const int slot = ns % RA_NS;
+                        key = max(max(key + 2, top + 1), endlv[slot] + top);
+                        const int base = key - top;
+                        endlv[slot] = base + applied;
+                        nlev = max(nlev, base + applied - 1);
+                        SweepRec* rec = sw + ns;
+                        rec->q0 = nrot, rec->top = top, rec->cnt = applied, rec->base = base;
+                        ++ns;
+                        nrot += applied;
+                    }
+                }
+            }
+            __syncwarp();
+            if (__shfl_sync(0xffffffffu, st0, 0)) {
+                status = 1;
+                break;
+            }
+        }
+    }
+    nrot = __shfl_sync(0xffffffffu, nrot, 0);
+    ns = __shfl_sync(0xffffffffu, ns, 0);
+    nlev = __shfl_sync(0xffffffffu, nlev, 0);
+    if (status == 0 && nlev > lcap) status = 1;
+    for (int i = lane; i < r; i += 32) lamall[(size_t)b * r + i] = de[i].x;
+    if (lane == 0) {
+        int32_t* meta = metaall + (size_t)b * 4;
+        meta[0] = ns;
+        meta[1] = nlev;
+        meta[2] = iters;
+        meta[3] = status | (rev ? 0x100 : 0);
+    }
+    if (status != 0) return;
+    // copy the first eight (c, s) of every sweep into its record
+    for (int q = lane; q < ns; q += 32) {
+        SweepRec* rec = sw + q;
+        const int q0 = rec->q0, cnt = rec->cnt;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rec->p[u] = u < cnt ? cs[q0 + u] : make_float2(1.f, 0.f);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- 4. apply the rotations to a slab of RA_C columns of Xt held in shared memory, level by level (one barrier per
+//         level). Slot q (RA_C lanes) follows the sweeps q, q + NS, q + 2 NS, ...: at level base + u it rotates rows
+//         (top - u, top - u + 1); the row shared by consecutive rotations stays in a register, so a rotation costs one
+//         shared-memory load and one store per column. The four slots of a warp work two rows apart: the 64-byte row
+//         halves of each 128-byte line are XOR-swizzled with bit 1 of the row so that they hit disjoint banks.
+//         (c, s) come from a 16-entry FIFO per slot that cp.async refills one block of eight ahead; the record of the
+//         slot's next sweep and its first block arrive the same way in private cells. Nothing in the loop waits on a
+//         global load. Then W[i][:] = lambda_i conj(Xt[i][:]). -------------------------------------------------------
+// Each lane owns two adjacent columns (one float4): a slot's row is 128 bytes = all 32 banks, conflict-free.
+__global__ void __launch_bounds__(RA_THREADS, 3) rotapply_kernel(const float2* __restrict__ Xall, int r,
+                                                                 const float2* __restrict__ csall,
+                                                                 const SweepRec* __restrict__ swall,
+                                                                 const int32_t* __restrict__ metaall,
+                                                                 const float* __restrict__ lamall,
+                                                                 float2* __restrict__ Wall, int ld, size_t wstride,
+                                                                 int cap, int scap, int32_t* __restrict__ done,
+                                                                 int32_t* __restrict__ sweeps) {
+    extern __shared__ float4 ra_sm[];
+    constexpr int C = RA_C;        // lanes per slot
+    constexpr int CW = 2 * RA_C;   // columns per slab
+    static_assert(C == 8, "parameter blocks of eight");
+    int4* hdrs = reinterpret_cast<int4*>(ra_sm);                    // [RA_THREADS] next sweep's record
+    float2* nfirst = reinterpret_cast<float2*>(hdrs + RA_THREADS);  // [RA_THREADS] its first block, per lane
+    float2* prm = nfirst + RA_THREADS;                              // [RA_NS][16] parameter FIFO per slot
+    float4* S = reinterpret_cast<float4*>(prm + RA_NS * 16);        // slab [r][C] float4 = two complex columns
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int32_t* meta = metaall + (size_t)b * 4;
+    const int ns = meta[0], nlev = meta[1], status = meta[3] & 0xff;
+    const bool rev = (meta[3] & 0x100) != 0;
+    if (blockIdx.x == 0 && tid == 0) {
+        done[b] = status == 0 ? 1 : 0;
+        sweeps[b] = meta[2];
+    }
+    if (status != 0) return;
+    const int col0 = blockIdx.x * CW;
+    const float2* X = Xall + (size_t)b * r * r;
+    float2* S2 = reinterpret_cast<float2*>(S);
+    for (int idx = tid; idx < r * CW; idx += RA_THREADS) {
+        const int i = idx / CW, c2 = idx - i * CW;
+        const int src = rev ? r - 1 - i : i;  // the QL iteration ran on the index-reversed tridiagonal
+        S2[idx] = (col0 + c2 < r) ? X[(size_t)src * r + col0 + c2] : make_float2(0.f, 0.f);
+    }
+    const float2* cs = csall + (size_t)b * cap;
+    const SweepRec* sw = swall + (size_t)b * scap;
+    const int slot = tid / C, cc = tid % C;
+    float2* myprm = prm + slot * 16;
+    float4* Scc = S + cc;
+    int s = slot;
+    int q0 = 0, top = 0, cnt = 0, u = -0x40000000;  // u = level - base of the current sweep
+    if (s < ns) {
+        const SweepRec* rec = sw + s;
+        q0 = rec->q0, top = rec->top, cnt = rec->cnt, u = -rec->base;
+        myprm[cc] = rec->p[cc];
+        if (8 + cc < cnt) cp_async8(&myprm[8 + cc], cs + q0 + 8 + cc);
+    }
+    if (s + RA_NS < ns) {
+        const SweepRec* rec = sw + s + RA_NS;
+        cp_async16(&hdrs[tid], rec);
+        cp_async8(&nfirst[tid], &rec->p[cc]);
+    }
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int lv = 1; lv <= nlev; ++lv) {
+        ++u;
+        if ((unsigned)u < (unsigned)cnt) {
+            const float2 p = myprm[u & 15];  // (c, s), broadcast within the slot
+            const int i = top - u;
+            if (u == 0) hi = Scc[(top + 1) * C];
+            const float4 a = Scc[i * C];
+            Scc[(i + 1) * C] = make_float4(fmaf(p.y, a.x, p.x * hi.x), fmaf(p.y, a.y, p.x * hi.y),
+                                           fmaf(p.y, a.z, p.x * hi.z), fmaf(p.y, a.w, p.x * hi.w));
+            hi = make_float4(fmaf(p.x, a.x, -p.y * hi.x), fmaf(p.x, a.y, -p.y * hi.y), fmaf(p.x, a.z, -p.y * hi.z),
+                             fmaf(p.x, a.w, -p.y * hi.w));
+            const int k8 = u & 7;
+            if (u == cnt - 1) {
+                Scc[i * C] = hi;
+                // the slot's next sweep: its record has been in the cells since the previous switch
+                s += RA_NS;
+                if (s < ns) {
+                    cp_async_wait_all();
+                    const int4 hd = hdrs[tid];
+                    q0 = hd.x, top = hd.y, cnt = hd.z, u = lv - hd.w;
+                    myprm[cc] = nfirst[tid];
+                    if (8 + cc < cnt) cp_async8(&myprm[8 + cc], cs + q0 + 8 + cc);
+                    if (s + RA_NS < ns) {
+                        const SweepRec* rec = sw + s + RA_NS;
+                        cp_async16(&hdrs[tid], rec);
+                        cp_async8(&nfirst[tid], &rec->p[cc]);
+                    }
+                } else {
+                    cnt = 0;
+                }
+            } else if (k8 == 7) {
+                cp_async_wait_all();  // block (u + 1) / 8 is complete; the level barrier publishes it to the slot
+            } else if (k8 == 0 && u >= 8) {
+                // block u / 8 is in use: the other half of the FIFO is free for block u / 8 + 1
+                const int nb = u + 8 + cc;
+                if (nb < cnt) cp_async8(&myprm[nb & 15], cs + q0 + nb);
+            }
+        }
+        __syncthreads();
+    }
+    float2* Wm = Wall + (size_t)b * wstride;
+    const float* lam = lamall + (size_t)b * r;
+    for (int idx = tid; idx < r * CW; idx += RA_THREADS) {
+        const int i = idx / CW, c2 = idx - i * CW;
+        if (col0 + c2 < r) {
+            const float l = lam[i];
+            const float2 v = S2[idx];
+            Wm[(size_t)i * ld + col0 + c2] = make_float2(l * v.x, -l * v.y);
+        }
+    }
+}
+
+inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+struct EigScratch {
+    size_t X, d, e, tau, ph, lam, cs, sw, meta, total;
+    int cap, scap, lcap;
+};
+
+EigScratch eig_layout(int B, int r) {
+    EigScratch s;
+    s.cap = (int)(((size_t)3 * r * r) / 2 + 256);
+    s.scap = 8 * r + 64;
+    s.lcap = 1 << 30;
+    size_t off = 0;
+    s.X = off, off += al((size_t)B * r * r * 8);
+    s.d = off, off += al((size_t)B * r * 4);
+    s.e = off, off += al((size_t)B * r * 4);
+    s.tau = off, off += al((size_t)B * r * 4);
+    s.ph = off, off += al((size_t)B * r * 8);
+    s.lam = off, off += al((size_t)B * r * 4);
+    s.cs = off, off += al((size_t)B * s.cap * 8);
+    s.sw = off, off += al((size_t)B * s.scap * sizeof(SweepRec));
+    s.meta = off, off += al((size_t)B * 16);
+    s.total = off;
+    return s;
+}
+
+template <int EPL, int RB>
+int launch_tridiag(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
+                   float* tau, float2* ph) {
+    const size_t smem = (size_t)5 * EPL * 32 * sizeof(float2);
+    VK_CUDA(h, cudaFuncSetAttribute(tridiag_kernel<EPL, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tridiag_kernel<EPL, RB><<<B, TD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+template <int EPL, int RPW>
+int launch_formq(vk_context* h, cudaStream_t st, const float2* W, int B, int r, int ld, size_t wstride, const float* tau,
+                 const float2* ph, float2* X) {
+    const size_t smem = (size_t)FQ_TJ * EPL * 32 * sizeof(float2);
+    VK_CUDA(h, cudaFuncSetAttribute(formq_kernel<EPL, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((r + FQ_WARPS * RPW - 1) / (FQ_WARPS * RPW), B);
+    formq_kernel<EPL, RPW><<<grid, FQ_THREADS, smem, st>>>(W, r, ld, wstride, tau, ph, X);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int launch_rotapply(vk_context* h, cudaStream_t st, const float2* X, int B, int r, const EigScratch& L,
+                    unsigned char* sc, float2* W, int ld, size_t wstride, int32_t* done, int32_t* sweeps) {
+    const size_t smem = (size_t)RA_THREADS * 24 + (size_t)RA_NS * 16 * 8 + (size_t)r * RA_C * sizeof(float4);
+    VK_CUDA(h, cudaFuncSetAttribute(rotapply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((r + 2 * RA_C - 1) / (2 * RA_C), B);
+    rotapply_kernel<<<grid, RA_THREADS, smem, st>>>(X, r, reinterpret_cast<const float2*>(sc + L.cs),
+                                                    reinterpret_cast<const SweepRec*>(sc + L.sw),
+                                                    reinterpret_cast<const int32_t*>(sc + L.meta),
+                                                    reinterpret_cast<const float*>(sc + L.lam), W, ld, wstride, L.cap,
+                                                    L.scap, done, sweeps);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+}  // namespace
+
+bool vk_eigqr_supported(int r) { return r >= 2 && r <= 1024; }
+
+size_t vk_eigqr_scratch_bytes(int B, int r) { return eig_layout(B, r).total; }
+
+// W [B][r][ld] in/out (see the header comment); scratch: vk_eigqr_scratch_bytes(B, r) bytes of device memory.
+// done_dev[b] = 1 / sweeps_dev[b] = QL iterations on success; done_dev[b] = 0 when the rotation store overflowed or
+// the QL iteration did not converge (W[b] is then left tridiagonalised, i.e. unusable).
+int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
+                    int32_t* done_dev) {
+    if (B <= 0) return VK_OK;
+    if (!vk_eigqr_supported(r)) return vk_fail(h, VK_EINVAL, "eig_impl=2 does not support this size");
+    const EigScratch L = eig_layout(B, r);
+    unsigned char* sc = static_cast<unsigned char*>(scratch);
+    cudaStream_t st = h->stream;
+    const size_t wstride = (size_t)r * ld;
+    float* d = reinterpret_cast<float*>(sc + L.d);
+    float* e = reinterpret_cast<float*>(sc + L.e);
+    float* tau = reinterpret_cast<float*>(sc + L.tau);
+    float2* ph = reinterpret_cast<float2*>(sc + L.ph);
+    float2* X = reinterpret_cast<float2*>(sc + L.X);
+    int rc;
+    const bool dbg = h->stage_timing >= 2;  // debug: serial execution, per-kernel event times on stderr
+    cudaEvent_t ev[5];
+    if (dbg) {
+        for (auto& x : ev) cudaEventCreate(&x);
+        cudaEventRecord(ev[0], st);
+    }
+    if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r <= 128) rc = launch_tridiag<4, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r <= 256) rc = launch_tridiag<8, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r <= 512) rc = launch_tridiag<16, 2>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else rc = launch_tridiag<32, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    if (rc) return rc;
+    if (dbg) cudaEventRecord(ev[1], st);
+    // the scalar QL iteration is latency bound (one lane per matrix): it runs alone - sharing the SMs with another
+    // kernel slows its dependent chain by more than the overlap wins (measured: 10.3 ms serial, 18.6 ms overlapped)
+    {
+        const size_t smem = (size_t)2 * (r + 2) * 4 + (size_t)RA_NS * 4;
+        VK_CUDA(h, cudaFuncSetAttribute(tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tql_kernel<<<B, 32, smem, st>>>(r, d, e, reinterpret_cast<float*>(sc + L.lam),
+                                               reinterpret_cast<float2*>(sc + L.cs), reinterpret_cast<SweepRec*>(sc + L.sw),
+                                               reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap);
+        VK_LAUNCH_CHECK(h);
+    }
+    if (dbg) cudaEventRecord(ev[2], st);
+    if (r <= 64) rc = launch_formq<2, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
+    else if (r <= 128) rc = launch_formq<4, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
+    else if (r <= 256) rc = launch_formq<8, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
+    else if (r <= 512) rc = launch_formq<16, 2>(h, st, W, B, r, ld, wstride, tau, ph, X);
+    else rc = launch_formq<32, 1>(h, st, W, B, r, ld, wstride, tau, ph, X);
+    if (rc) return rc;
+    if (dbg) cudaEventRecord(ev[3], st);
+    rc = launch_rotapply(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev);
+    if (dbg) {
+        cudaEventRecord(ev[4], st);
+        cudaEventSynchronize(ev[4]);
+        float t[4];
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+        fprintf(stderr, "[eigqr B=%d r=%d] tridiag %.3f  tql %.3f  formq %.3f  rotapply %.3f ms\n", B, r, t[0], t[1], t[2], t[3]);
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    return rc;
+}
