@@ -422,3 +422,31 @@ def test_internal_scheduling_options_do_not_change_results(eng, torch):
     finally:
         for k_ in keys:
             eng.set_option(k_, 0)
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_multiple_and_clustered_leading_singular_values(eng, k):
+    """Fixed rank on the Gram path with exactly multiple, nearly multiple and vanishing leading singular values: the
+    leading-eigenpair path (bisection + twisted factorisation) has to hand true clusters to the full solver and still
+    return an orthonormal basis of the optimal subspace."""
+    from visco_b200.compress_ms import apply_svd
+    from visco_b200.decompress_ms import reconstruct_vis
+    rng = np.random.default_rng(3)
+    m, n = 128, 256
+    Q1, _ = np.linalg.qr(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    cases = [np.ones(m),
+             np.concatenate([[5, 5, 5, 2, 1], 0.01 * np.ones(m - 5)]),
+             np.concatenate([[5, 5 * (1 - 1e-6), 3, 2, 1], 0.01 * rng.random(m - 5)]),
+             np.concatenate([[5, 5 * (1 - 1e-4), 3, 2, 1], 0.01 * rng.random(m - 5)]),
+             np.concatenate([[3, 1], np.zeros(m - 2)])]
+    for sv in cases:
+        A = ((Q1 * sv[None, :]) @ Q2[:m]).astype(np.complex64)
+        U, S, Vt = apply_svd(A, compressionrank=k)
+        s_sorted = np.sort(sv)[::-1]
+        np.testing.assert_allclose(S, s_sorted[:k], rtol=1e-4, atol=2e-6 * s_sorted[0])
+        rec = reconstruct_vis(U, S, Vt)
+        optimal = np.sqrt(np.sum(s_sorted[k:] ** 2))
+        err = np.linalg.norm(A.astype(np.complex128) - rec)
+        assert abs(err - optimal) <= 1e-5 * optimal + 5e-6 * np.linalg.norm(A), (sv[:5], err, optimal)
+        assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-4

@@ -19,13 +19,13 @@ bool small_path(int m, int n) {
     return (size_t)(r + (r & 1)) * (size_t)(L + r) * sizeof(float2) + 1024 <= VK_SMEM_BUDGET;
 }
 
-// eigensolver of the Gram path: 2 = tridiagonalisation + implicit QL, 1 = cyclic Jacobi, 0 = auto (QL where it is
-// supported, except for fixed ranks the blocked subspace iteration handles)
+// eigensolver of the Gram path: 1 = cyclic Jacobi (with the blocked subspace iteration for small fixed ranks),
+// 0 / 2 = tridiagonalisation + implicit QL where the size is supported (leading pairs only for small fixed ranks)
 bool use_qr(const vk_context* h, int m, int n, int fixed_rank = 0) {
+    (void)fixed_rank;
     const int r = m < n ? m : n;
     if (!h || small_path(m, n) || !vk_eigqr_supported(r) || h->eig_impl == 1) return false;
-    if (h->eig_impl == 2) return true;
-    return !(h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2));
+    return true;
 }
 
 WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false) {
@@ -59,11 +59,10 @@ int auto_chunk(const vk_context* h, int B, int m, int n, bool qr) {
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
     if (qr) {
-        // the direct solver runs one CTA per matrix in its first stage: two waves of matrices per pass, bounded by
-        // 8 GB of rotation scratch
-        size_t c = 2 * (size_t)(h ? h->num_sms : 148);
-        const size_t per = vk_eigqr_scratch_bytes(1, r);
-        if (c * per > ((size_t)8 << 30)) c = ((size_t)8 << 30) / per;
+        // the direct solver has a latency-bound stage (the scalar QL iteration, one lane per matrix) whose duration
+        // does not depend on the number of matrices: take as many per pass as 8 GB of scratch allow
+        const size_t per = vk_eigqr_scratch_bytes(1, r) + (size_t)r * r * 8;
+        size_t c = ((size_t)8 << 30) / per;
         if (c < 1) c = 1;
         if (c > (size_t)B) c = B;
         return (int)c;
@@ -178,7 +177,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         tm.mark(1);
         // fixed small rank: blocked subspace iteration first; the full Jacobi solver only sees what it left unsolved
         if (use_qr(h, m, n, fixed_rank)) {
-            if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done))) return rc;
+            if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done, fixed_rank))) return rc;
         } else {
             const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
             if (fast && (rc = vk_launch_topk(h, W, B, r, fixed_rank, done, sweeps))) return rc;

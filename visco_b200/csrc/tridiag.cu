@@ -11,6 +11,7 @@
 // Xt holds (Q D Z)^T: row i is eigenvector i, so a plane rotation of columns (i, i+1) of Z acts on rows i, i+1 of Xt.
 // On exit W[b][i][:] = lambda_i * conj(Xt[i][:]) - the layout the Jacobi solver leaves (vectors of norm lambda_i).
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -232,11 +233,12 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
 template <int EPL, int RPW>
 __global__ void __launch_bounds__(FQ_THREADS, (EPL <= 16) ? 2 : 1)
     formq_kernel(const float2* __restrict__ Wall, int r, int ld, size_t wstride, const float* __restrict__ tauall,
-                 const float2* __restrict__ phall, float2* __restrict__ Xall) {
+                 const float2* __restrict__ phall, float2* __restrict__ Xall, const int32_t* __restrict__ skip) {
     constexpr int WIDTH = EPL * 32;
     extern __shared__ float2 fq_sv[];  // [FQ_TJ][WIDTH]
     __shared__ float stau[FQ_TJ];
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (skip && skip[b]) return;
     const float2* M = Wall + (size_t)b * wstride;
     const float* taus = tauall + (size_t)b * r;
     const int rbase = blockIdx.x * (FQ_WARPS * RPW);
@@ -339,11 +341,12 @@ struct SweepRec {
 __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict__ dall, const float* __restrict__ eall,
                                                  float* __restrict__ lamall, float2* __restrict__ csall,
                                                  SweepRec* __restrict__ swall, int32_t* __restrict__ metaall, int cap,
-                                                 int scap, int lcap) {
+                                                 int scap, int lcap, const int32_t* __restrict__ skip) {
     extern __shared__ float ql_sm[];
     float2* de = reinterpret_cast<float2*>(ql_sm) + 1;  // de[i] = (d_i, e_i), i = -1 .. r-1 (de[-1] is a pad)
     int* endlv = reinterpret_cast<int*>(ql_sm + 2 * (r + 2));  // [RA_NS] end level of the last sweep of each slot
     const int b = blockIdx.x, lane = threadIdx.x;
+    if (skip && skip[b]) return;
     float2* cs = csall + (size_t)b * cap;
     SweepRec* sw = swall + (size_t)b * scap;
     // QL deflates from the top and needs the large entries at the bottom (LAPACK steqr picks QL or QR by the same
@@ -503,8 +506,10 @@ __global__ void __launch_bounds__(RA_THREADS, 3) rotapply_kernel(const float2* _
                                                                  const float* __restrict__ lamall,
                                                                  float2* __restrict__ Wall, int ld, size_t wstride,
                                                                  int cap, int scap, int32_t* __restrict__ done,
-                                                                 int32_t* __restrict__ sweeps) {
+                                                                 int32_t* __restrict__ sweeps,
+                                                                 const int32_t* __restrict__ skip) {
     extern __shared__ float4 ra_sm[];
+    if (skip && skip[blockIdx.y]) return;
     constexpr int C = RA_C;        // lanes per slot
     constexpr int CW = 2 * RA_C;   // columns per slab
     static_assert(C == 8, "parameter blocks of eight");
@@ -601,10 +606,271 @@ __global__ void __launch_bounds__(RA_THREADS, 3) rotapply_kernel(const float2* _
     }
 }
 
+// =====================================================================================================================
+// Fixed small rank (compressionrank <= TK_MAXK): only the k leading eigenpairs are needed, so after the
+// tridiagonalisation the QL iteration, the reflector accumulation and the rotation application are replaced by
+//   (a) Sturm bisection for the k+1 largest eigenvalues of T (one thread per eigenvalue),
+//   (b) one twisted factorisation per eigenvalue for its eigenvector of T, then modified Gram-Schmidt,
+//   (c) the reflectors applied to those k vectors only.
+// Close eigenvalues only mix their own vectors (angle ~ eps / gap), which Gram-Schmidt keeps orthonormal and which
+// changes neither the retained subspace nor, to second order, the refined singular values; what must be avoided is two
+// lanes converging to the same vector (numerically multiple eigenvalues). That is detected directly: a vector that
+// loses more than 3/4 of its squared length in the Gram-Schmidt step sends the matrix to the full path, as does a
+// non-positive leading eigenvalue or overflowing element growth. flag[b] = 0 makes (b)/(c) skip the matrix and the
+// full-path kernels take it; flag[b] = 1 makes those skip it.
+constexpr int TK_MAXK = 32;
+constexpr float TK_GAP = 0.f;  // eigenvalue-gap pre-test (relative to lambda_max); 0: rely on the duplicate test
+
+__device__ __forceinline__ int sturm_count(const float* d, const float* e2, int r, float x, float pivmin) {
+    // number of eigenvalues of T smaller than x
+    int c = 0;
+    float q = d[0] - x;
+    if (fabsf(q) < pivmin) q = -pivmin;
+    c += q < 0.f;
+    for (int i = 1; i < r; ++i) {
+        q = d[i] - x - e2[i - 1] / q;
+        if (fabsf(q) < pivmin) q = -pivmin;
+        c += q < 0.f;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(64) bisect_kernel(int r, int nev, const float* __restrict__ dall,
+                                                    const float* __restrict__ eall, float* __restrict__ lamtop,
+                                                    int32_t* __restrict__ flag, float gap) {
+    extern __shared__ float bs_sm[];
+    float* d = bs_sm;
+    float* e2 = bs_sm + r;
+    __shared__ float s_lo[2], s_hi[2], s_lam[TK_MAXK + 1];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float lo = 3.4e38f, hi = -3.4e38f;
+    for (int i = tid; i < r; i += 64) {
+        const float di = dall[(size_t)b * r + i];
+        const float ei = i < r - 1 ? eall[(size_t)b * r + i] : 0.f;
+        const float ep = i > 0 ? eall[(size_t)b * r + i - 1] : 0.f;
+        d[i] = di;
+        e2[i] = ei * ei;
+        const float rad = fabsf(ei) + fabsf(ep);
+        lo = fminf(lo, di - rad);
+        hi = fmaxf(hi, di + rad);
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    if ((tid & 31) == 0) s_lo[tid >> 5] = lo, s_hi[tid >> 5] = hi;
+    __syncthreads();
+    lo = fminf(s_lo[0], s_lo[1]);
+    hi = fmaxf(s_hi[0], s_hi[1]);
+    const float scale = fmaxf(fabsf(lo), fabsf(hi));
+    const float pivmin = fmaxf(1e-30f, 1e-14f * scale * scale);
+    if (tid < nev) {
+        // eigenvalue number idx in ascending order: the smallest x with count(x) > idx
+        const int idx = r - 1 - tid;
+        float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+        for (int it = 0; it < 48; ++it) {
+            const float mid = 0.5f * (a + c);
+            if (!(mid > a && mid < c)) break;
+            if (sturm_count(d, e2, r, mid, pivmin) > idx) c = mid;
+            else a = mid;
+        }
+        const float lam = 0.5f * (a + c);
+        s_lam[tid] = lam;
+        lamtop[(size_t)b * (TK_MAXK + 1) + tid] = lam;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        bool ok = s_lam[0] > 0.f;
+        const float thr = gap * fabsf(s_lam[0]);
+        for (int t = 0; t + 1 < nev; ++t) ok = ok && (s_lam[t] - s_lam[t + 1] >= thr);
+        flag[b] = ok ? 1 : 0;
+    }
+}
+
+// eigenvectors of T by twisted factorisation (one lane per eigenvalue), then modified Gram-Schmidt over the k vectors
+__global__ void __launch_bounds__(32) twisted_kernel(int r, int k, const float* __restrict__ dall,
+                                                     const float* __restrict__ eall, const float* __restrict__ lamtop,
+                                                     int32_t* __restrict__ flag, float* __restrict__ zall,
+                                                     float* __restrict__ dmall) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (flag[b] == 0) return;
+    const float* d = dall + (size_t)b * r;
+    const float* e = eall + (size_t)b * r;
+    float* zb = zall + (size_t)b * TK_MAXK * r;
+    int bad = 0;
+    if (lane < k) {
+        const float lam = lamtop[(size_t)b * (TK_MAXK + 1) + lane];
+        float* z = zb + (size_t)lane * r;
+        float* dm = dmall + ((size_t)b * TK_MAXK + lane) * r;
+        const float pivmin = fmaxf(1e-30f, 1e-14f * lam * lam);
+        // backward pivots dm[i] of U D- U^T = T - lam
+        float q = d[r - 1] - lam;
+        if (fabsf(q) < pivmin) q = -pivmin;
+        dm[r - 1] = q;
+        for (int i = r - 2; i >= 0; --i) {
+            const float ei = e[i];
+            q = d[i] - lam - ei * ei / q;
+            if (fabsf(q) < pivmin) q = -pivmin;
+            dm[i] = q;
+        }
+        // forward pivots dp[i] of L D+ L^T (kept in z for now) and the twist index: argmin |gamma_i|,
+        // gamma_i = dp[i] + dm[i] - (d[i] - lam)
+        float p = d[0] - lam;
+        if (fabsf(p) < pivmin) p = -pivmin;
+        z[0] = p;
+        float best = fabsf(dm[0]);  // gamma_0 = dm[0]
+        int kt = 0;
+        for (int i = 1; i < r; ++i) {
+            const float ei = e[i - 1];
+            p = d[i] - lam - ei * ei / p;
+            if (fabsf(p) < pivmin) p = -pivmin;
+            z[i] = p;
+            const float gam = fabsf(p + dm[i] - (d[i] - lam));
+            if (gam < best) best = gam, kt = i;
+        }
+        // z[kt] = 1; upward with the forward pivots, downward with the backward ones
+        float nrm = 1.f, zi = 1.f;
+        for (int i = kt - 1; i >= 0; --i) {
+            zi = -(e[i] / z[i]) * zi;  // z[i] still holds dp[i]
+            z[i] = zi;
+            nrm = fmaf(zi, zi, nrm);
+        }
+        zi = 1.f;
+        for (int i = kt + 1; i < r; ++i) {
+            zi = -(e[i - 1] / dm[i]) * zi;
+            z[i] = zi;
+            nrm = fmaf(zi, zi, nrm);
+        }
+        z[kt] = 1.f;
+        const float sc = rsqrtf(nrm);
+        for (int i = 0; i < r; ++i) z[i] *= sc;
+        if (!(nrm < 3e38f)) bad = 1;  // element growth overflowed: leave the matrix to the full path
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+        if (lane == 0) flag[b] = 0;
+        return;
+    }
+    // modified Gram-Schmidt in order of decreasing eigenvalue (all lanes cooperate, entries strided over lanes)
+    for (int t = 0; t < k; ++t) {
+        float* zt = zb + (size_t)t * r;
+        for (int s = 0; s < t; ++s) {
+            const float* zs = zb + (size_t)s * r;
+            float dot = 0.f;
+            for (int i = lane; i < r; i += 32) dot = fmaf(zs[i], zt[i], dot);
+            dot = warp_sum(dot);
+            for (int i = lane; i < r; i += 32) zt[i] = fmaf(-dot, zs[i], zt[i]);
+            __syncwarp();
+        }
+        float nn = 0.f;
+        for (int i = lane; i < r; i += 32) nn = fmaf(zt[i], zt[i], nn);
+        nn = warp_sum(nn);
+        if (!(nn >= 0.25f)) {
+            // this vector (unit length before) was mostly a copy of earlier ones: numerically multiple eigenvalue,
+            // the twisted factorisations converged to the same vector. The full path handles clusters.
+            if (lane == 0) flag[b] = 0;
+            return;
+        }
+        const float sc = nn > 0.f ? rsqrtf(nn) : 0.f;
+        for (int i = lane; i < r; i += 32) zt[i] *= sc;
+        __syncwarp();
+    }
+}
+
+// v_t = Q D z_t for the k vectors of one matrix (one CTA; warp w takes vectors w*RPW ..), then
+// W[t][:] = lambda_t conj(v_t) for t < k and zero rows below: what the selection and factor stages expect.
+template <int EPL, int RPW>
+__global__ void __launch_bounds__(FQ_THREADS, (EPL * RPW <= 32) ? 2 : 1)
+    backtr_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, int k, const float* __restrict__ tauall,
+                  const float2* __restrict__ phall, const float* __restrict__ zall, const float* __restrict__ lamtop,
+                  const int32_t* __restrict__ flag, int32_t* __restrict__ done, int32_t* __restrict__ sweeps) {
+    constexpr int WIDTH = EPL * 32;
+    extern __shared__ float2 fq_sv[];  // [FQ_TJ][WIDTH]
+    __shared__ float stau[FQ_TJ];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (flag[b] == 0) return;
+    float2* M = Wall + (size_t)b * wstride;
+    const float* taus = tauall + (size_t)b * r;
+    const int i0 = warp * RPW;
+    float2 y[RPW][EPL];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q)
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int kk = e * 32 + lane;
+            float2 v = make_float2(0.f, 0.f);
+            if (i0 + q < k && kk < r) {
+                const float z = zall[((size_t)b * TK_MAXK + i0 + q) * r + kk];
+                const float2 p = phall[(size_t)b * r + kk];
+                v = make_float2(z * p.x, z * p.y);
+            }
+            y[q][e] = v;
+        }
+    for (int jt = r - 3; jt >= 0; jt -= FQ_TJ) {
+        __syncthreads();
+        for (int idx = tid; idx < FQ_TJ * WIDTH; idx += FQ_THREADS) {
+            const int t = idx / WIDTH, kk = idx - t * WIDTH, j = jt - t;
+            float2 v = make_float2(0.f, 0.f);
+            if (j >= 0 && kk > j && kk < r) v = M[(size_t)j * ld + kk];
+            fq_sv[idx] = v;
+        }
+        if (tid < FQ_TJ) stau[tid] = (jt - tid >= 0) ? taus[jt - tid] : 0.f;
+        __syncthreads();
+        if (i0 >= k) continue;
+#pragma unroll 1
+        for (int t = 0; t < FQ_TJ; ++t) {
+            const int j = jt - t;
+            if (j < 0) break;
+            const float tau = stau[t];
+            if (tau == 0.f) continue;
+            const int e0 = (j + 1) >> 5;
+            float2 v[EPL];
+#pragma unroll
+            for (int e = 0; e < EPL; ++e)
+                if (e >= e0) v[e] = fq_sv[t * WIDTH + e * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                float2 u = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (e >= e0) {
+                        u.x = fmaf(v[e].x, y[q][e].x, fmaf(v[e].y, y[q][e].y, u.x));
+                        u.y = fmaf(v[e].x, y[q][e].y, fmaf(-v[e].y, y[q][e].x, u.y));
+                    }
+                u.x = tau * warp_sum(u.x);
+                u.y = tau * warp_sum(u.y);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (e >= e0) {
+                        y[q][e].x = fmaf(-u.x, v[e].x, fmaf(u.y, v[e].y, y[q][e].x));
+                        y[q][e].y = fmaf(-u.x, v[e].y, fmaf(-u.y, v[e].x, y[q][e].y));
+                    }
+            }
+        }
+    }
+    __syncthreads();  // every reflector has been read: the rows of M can be overwritten
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+        const int t = i0 + q;
+        if (t >= k) continue;
+        const float lam = lamtop[(size_t)b * (TK_MAXK + 1) + t];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const int kk = e * 32 + lane;
+            if (kk < r) M[(size_t)t * ld + kk] = make_float2(lam * y[q][e].x, -lam * y[q][e].y);
+        }
+    }
+    for (int idx = tid; idx < (r - k) * r; idx += FQ_THREADS) {
+        const int row = k + idx / r, kk = idx % r;
+        M[(size_t)row * ld + kk] = make_float2(0.f, 0.f);
+    }
+    if (tid == 0) {
+        done[b] = 1;
+        sweeps[b] = 0;
+    }
+}
+
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct EigScratch {
-    size_t X, d, e, tau, ph, lam, cs, sw, meta, total;
+    size_t X, d, e, tau, ph, lam, cs, sw, meta, lamtop, flag, z, dm, total;
     int cap, scap, lcap;
 };
 
@@ -623,6 +889,10 @@ EigScratch eig_layout(int B, int r) {
     s.cs = off, off += al((size_t)B * s.cap * 8);
     s.sw = off, off += al((size_t)B * s.scap * sizeof(SweepRec));
     s.meta = off, off += al((size_t)B * 16);
+    s.lamtop = off, off += al((size_t)B * (TK_MAXK + 1) * 4);
+    s.flag = off, off += al((size_t)B * 4);
+    s.z = off, off += al((size_t)B * TK_MAXK * r * 4);
+    s.dm = off, off += al((size_t)B * TK_MAXK * r * 4);
     s.total = off;
     return s;
 }
@@ -639,17 +909,18 @@ int launch_tridiag(vk_context* h, cudaStream_t st, float2* W, int B, int r, int 
 
 template <int EPL, int RPW>
 int launch_formq(vk_context* h, cudaStream_t st, const float2* W, int B, int r, int ld, size_t wstride, const float* tau,
-                 const float2* ph, float2* X) {
+                 const float2* ph, float2* X, const int32_t* skip) {
     const size_t smem = (size_t)FQ_TJ * EPL * 32 * sizeof(float2);
     VK_CUDA(h, cudaFuncSetAttribute(formq_kernel<EPL, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((r + FQ_WARPS * RPW - 1) / (FQ_WARPS * RPW), B);
-    formq_kernel<EPL, RPW><<<grid, FQ_THREADS, smem, st>>>(W, r, ld, wstride, tau, ph, X);
+    formq_kernel<EPL, RPW><<<grid, FQ_THREADS, smem, st>>>(W, r, ld, wstride, tau, ph, X, skip);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
 
 int launch_rotapply(vk_context* h, cudaStream_t st, const float2* X, int B, int r, const EigScratch& L,
-                    unsigned char* sc, float2* W, int ld, size_t wstride, int32_t* done, int32_t* sweeps) {
+                    unsigned char* sc, float2* W, int ld, size_t wstride, int32_t* done, int32_t* sweeps,
+                    const int32_t* skip) {
     const size_t smem = (size_t)RA_THREADS * 24 + (size_t)RA_NS * 16 * 8 + (size_t)r * RA_C * sizeof(float4);
     VK_CUDA(h, cudaFuncSetAttribute(rotapply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((r + 2 * RA_C - 1) / (2 * RA_C), B);
@@ -657,9 +928,29 @@ int launch_rotapply(vk_context* h, cudaStream_t st, const float2* X, int B, int 
                                                     reinterpret_cast<const SweepRec*>(sc + L.sw),
                                                     reinterpret_cast<const int32_t*>(sc + L.meta),
                                                     reinterpret_cast<const float*>(sc + L.lam), W, ld, wstride, L.cap,
-                                                    L.scap, done, sweeps);
+                                                    L.scap, done, sweeps, skip);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
+}
+
+template <int EPL, int RPW>
+int launch_backtr(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, int k, const float* tau,
+                  const float2* ph, const EigScratch& L, unsigned char* sc, int32_t* done, int32_t* sweeps) {
+    const size_t smem = (size_t)FQ_TJ * EPL * 32 * sizeof(float2);
+    VK_CUDA(h, cudaFuncSetAttribute(backtr_kernel<EPL, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    backtr_kernel<EPL, RPW><<<B, FQ_THREADS, smem, st>>>(W, r, ld, wstride, k, tau, ph,
+                                                         reinterpret_cast<const float*>(sc + L.z),
+                                                         reinterpret_cast<const float*>(sc + L.lamtop),
+                                                         reinterpret_cast<const int32_t*>(sc + L.flag), done, sweeps);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+// largest fixed rank the leading-eigenpair path takes at this size (0 = none)
+int topk_qr_limit(int r) {
+    if (r < 4) return 0;
+    const int lim = r <= 512 ? TK_MAXK : TK_MAXK / 2;  // vectors per CTA of the back-transformation
+    return lim < r - 1 ? lim : r - 2;
 }
 
 }  // namespace
@@ -671,8 +962,10 @@ size_t vk_eigqr_scratch_bytes(int B, int r) { return eig_layout(B, r).total; }
 // W [B][r][ld] in/out (see the header comment); scratch: vk_eigqr_scratch_bytes(B, r) bytes of device memory.
 // done_dev[b] = 1 / sweeps_dev[b] = QL iterations on success; done_dev[b] = 0 when the rotation store overflowed or
 // the QL iteration did not converge (W[b] is then left tridiagonalised, i.e. unusable).
+// fixed_rank > 0 (and small enough): only the leading fixed_rank vectors are produced for matrices whose leading
+// eigenvalues are well separated (rows below are zero); the others take the full path.
 int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
-                    int32_t* done_dev) {
+                    int32_t* done_dev, int fixed_rank) {
     if (B <= 0) return VK_OK;
     if (!vk_eigqr_supported(r)) return vk_fail(h, VK_EINVAL, "eig_impl=2 does not support this size");
     const EigScratch L = eig_layout(B, r);
@@ -685,8 +978,8 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     float2* ph = reinterpret_cast<float2*>(sc + L.ph);
     float2* X = reinterpret_cast<float2*>(sc + L.X);
     int rc;
-    const bool dbg = h->stage_timing >= 2;  // debug: serial execution, per-kernel event times on stderr
-    cudaEvent_t ev[5];
+    const bool dbg = h->stage_timing >= 2;  // debug: per-kernel event times on stderr
+    cudaEvent_t ev[6];
     if (dbg) {
         for (auto& x : ev) cudaEventCreate(&x);
         cudaEventRecord(ev[0], st);
@@ -698,31 +991,52 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     else rc = launch_tridiag<32, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     if (rc) return rc;
     if (dbg) cudaEventRecord(ev[1], st);
+    const int32_t* skip = nullptr;
+    if (h->topk != 1 && fixed_rank > 0 && fixed_rank <= topk_qr_limit(r)) {
+        const int k = fixed_rank;
+        float* lamtop = reinterpret_cast<float*>(sc + L.lamtop);
+        int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
+        const char* genv = getenv("VK_TK_GAP");
+        bisect_kernel<<<B, 64, (size_t)2 * r * 4, st>>>(r, k + 1, d, e, lamtop, flag, genv ? (float)atof(genv) : TK_GAP);
+        VK_LAUNCH_CHECK(h);
+        twisted_kernel<<<B, 32, 0, st>>>(r, k, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
+                                         reinterpret_cast<float*>(sc + L.dm));
+        VK_LAUNCH_CHECK(h);
+        if (r <= 64) rc = launch_backtr<2, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        else if (r <= 128) rc = launch_backtr<4, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        else if (r <= 256) rc = launch_backtr<8, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        else if (r <= 512) rc = launch_backtr<16, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        else rc = launch_backtr<32, 2>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        if (rc) return rc;
+        skip = flag;  // the full path below takes what is left (flag 0)
+    }
+    if (dbg) cudaEventRecord(ev[2], st);
     // the scalar QL iteration is latency bound (one lane per matrix): it runs alone - sharing the SMs with another
     // kernel slows its dependent chain by more than the overlap wins (measured: 10.3 ms serial, 18.6 ms overlapped)
     {
         const size_t smem = (size_t)2 * (r + 2) * 4 + (size_t)RA_NS * 4;
         VK_CUDA(h, cudaFuncSetAttribute(tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tql_kernel<<<B, 32, smem, st>>>(r, d, e, reinterpret_cast<float*>(sc + L.lam),
-                                               reinterpret_cast<float2*>(sc + L.cs), reinterpret_cast<SweepRec*>(sc + L.sw),
-                                               reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap);
+                                        reinterpret_cast<float2*>(sc + L.cs), reinterpret_cast<SweepRec*>(sc + L.sw),
+                                        reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap, skip);
         VK_LAUNCH_CHECK(h);
     }
-    if (dbg) cudaEventRecord(ev[2], st);
-    if (r <= 64) rc = launch_formq<2, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
-    else if (r <= 128) rc = launch_formq<4, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
-    else if (r <= 256) rc = launch_formq<8, 4>(h, st, W, B, r, ld, wstride, tau, ph, X);
-    else if (r <= 512) rc = launch_formq<16, 2>(h, st, W, B, r, ld, wstride, tau, ph, X);
-    else rc = launch_formq<32, 1>(h, st, W, B, r, ld, wstride, tau, ph, X);
-    if (rc) return rc;
     if (dbg) cudaEventRecord(ev[3], st);
-    rc = launch_rotapply(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev);
+    if (r <= 64) rc = launch_formq<2, 4>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
+    else if (r <= 128) rc = launch_formq<4, 4>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
+    else if (r <= 256) rc = launch_formq<8, 4>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
+    else if (r <= 512) rc = launch_formq<16, 2>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
+    else rc = launch_formq<32, 1>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
+    if (rc) return rc;
+    if (dbg) cudaEventRecord(ev[4], st);
+    rc = launch_rotapply(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip);
     if (dbg) {
-        cudaEventRecord(ev[4], st);
-        cudaEventSynchronize(ev[4]);
-        float t[4];
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-        fprintf(stderr, "[eigqr B=%d r=%d] tridiag %.3f  tql %.3f  formq %.3f  rotapply %.3f ms\n", B, r, t[0], t[1], t[2], t[3]);
+        cudaEventRecord(ev[5], st);
+        cudaEventSynchronize(ev[5]);
+        float t[5];
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+        fprintf(stderr, "[eigqr B=%d r=%d k=%d] tridiag %.3f  leading-pairs %.3f  tql %.3f  formq %.3f  rotapply %.3f ms\n", B,
+                r, fixed_rank, t[0], t[1], t[2], t[3], t[4]);
         for (auto& x : ev) cudaEventDestroy(x);
     }
     return rc;
