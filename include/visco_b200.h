@@ -62,7 +62,10 @@ int vk_sync(vk_handle h);
  *          "stage_timing" (0/1, see vk_last_stage_ms), "topk" (0 = blocked subspace iteration for fixed rank <= 4 with
  *          fallback to the full solver, 1 = full solver only, 2 = also for ranks up to 8), "gemm_impl" (0 = tcgen05 GEMM for k > 8, 1 = SIMT),
  *          "small_reg" (1 = register-resident recursive-tournament kernel on the small path where the shape allows
- *          (default), 0 = shared-memory round-robin kernel only). */
+ *          (default), 0 = shared-memory round-robin kernel only),
+ *          "eig_impl" (Hermitian eigensolver of the Gram path: 0 = auto = 2 where min(m, n) <= 1024, 1 = one-sided cyclic
+ *          Jacobi, 2 = Householder tridiagonalisation + implicit QL; with 0/2 a fixed rank <= 32 takes only the leading
+ *          eigenpairs: Sturm bisection + twisted factorisation, unless "topk" = 1). */
 int vk_set_option(vk_handle h, const char* key, double value);
 /* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own
  * workspace when ws == NULL). */
@@ -147,6 +150,10 @@ int64_t vk_launch_count(vk_handle h);
  * handle's stream: t[0] gram, t[1] jacobi (all sweeps), t[2] select+truncate, t[3] factor formation (U/Vt),
  * t[4] small-path kernel, t[5] total. Requires option "stage_timing" = 1 (adds event records + one sync). */
 int vk_last_stage_ms(vk_handle h, float* t6);
+/* the eigen-solve slot t[1] of the last vk_compress_batched call split by kernel of the direct solver (option
+ * "eig_impl" != 1): t[0] tridiagonalisation, t[1] leading eigenpairs (fixed small rank), t[2] implicit QL,
+ * t[3] reflector accumulation, t[4] rotation application. Requires "stage_timing" = 1. */
+int vk_last_eig_ms(vk_handle h, float* t5);
 
 #ifdef __cplusplus
 }

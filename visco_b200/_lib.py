@@ -38,6 +38,7 @@ SIGNATURES = {
     "vk_synth_fill": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _u64]),
     "vk_launch_count": (C.c_int64, [_vp]),
     "vk_last_stage_ms": (_i, [_vp, C.POINTER(_f)]),
+    "vk_last_eig_ms": (_i, [_vp, C.POINTER(_f)]),
 }
 
 _lib = None

@@ -246,6 +246,7 @@ int vk_create(vk_handle* out, int device) {
     }
     std::memset(h->h_poll, 0, 64);
     for (auto& e : h->ev) cudaEventCreate(&e);
+    for (auto& e : h->eig_ev) cudaEventCreate(&e);
     *out = h;
     return VK_OK;
 }
@@ -258,6 +259,8 @@ int vk_destroy(vk_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : h->eig_ev)
         if (e) cudaEventDestroy(e);
     for (auto& s : h->sub)
         if (s) cudaStreamDestroy(s);
@@ -368,6 +371,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
         return vk_fail(h, VK_EINVAL, "workspace too small: need " + std::to_string(L.total) + " bytes");
     }
     for (int i = 0; i < 6; ++i) h->stage_ms[i] = 0.f;
+    for (int i = 0; i < 5; ++i) h->eig_ms[i] = 0.f;
     cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
     if (h->stage_timing) cudaEventRecord(e0, h->stream);
     const float2* Ap = static_cast<const float2*>(A);
@@ -634,6 +638,12 @@ int vk_synth_fill(vk_handle h, void* A, int nbl_local, int ncorr, int m, int n, 
 }
 
 int64_t vk_launch_count(vk_handle h) { return h ? h->launches : 0; }
+
+int vk_last_eig_ms(vk_handle h, float* t5) {
+    if (!h || !t5) return VK_EINVAL;
+    for (int i = 0; i < 5; ++i) t5[i] = h->eig_ms[i];
+    return VK_OK;
+}
 
 int vk_last_stage_ms(vk_handle h, float* t6) {
     if (!h || !t6) return VK_EINVAL;

@@ -44,6 +44,8 @@ struct vk_context {
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+    float eig_ms[5] = {0, 0, 0, 0, 0};  // direct eigensolver: tridiag, leading pairs, QL, reflector accumulation, rotations
+    cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -978,12 +978,9 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     float2* ph = reinterpret_cast<float2*>(sc + L.ph);
     float2* X = reinterpret_cast<float2*>(sc + L.X);
     int rc;
-    const bool dbg = h->stage_timing >= 2;  // debug: per-kernel event times on stderr
-    cudaEvent_t ev[6];
-    if (dbg) {
-        for (auto& x : ev) cudaEventCreate(&x);
-        cudaEventRecord(ev[0], st);
-    }
+    const bool dbg = h->stage_timing >= 1;  // per-kernel event times (vk_last_eig_ms; also on stderr at level 2)
+    cudaEvent_t* ev = h->eig_ev;
+    if (dbg) cudaEventRecord(ev[0], st);
     if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 128) rc = launch_tridiag<4, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 256) rc = launch_tridiag<8, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
@@ -1035,9 +1032,10 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         cudaEventSynchronize(ev[5]);
         float t[5];
         for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-        fprintf(stderr, "[eigqr B=%d r=%d k=%d] tridiag %.3f  leading-pairs %.3f  tql %.3f  formq %.3f  rotapply %.3f ms\n", B,
-                r, fixed_rank, t[0], t[1], t[2], t[3], t[4]);
-        for (auto& x : ev) cudaEventDestroy(x);
+        for (int i = 0; i < 5; ++i) h->eig_ms[i] += t[i];
+        if (h->stage_timing >= 2)
+            fprintf(stderr, "[eigqr B=%d r=%d k=%d] tridiag %.3f  leading-pairs %.3f  tql %.3f  formq %.3f  rotapply %.3f ms\n",
+                    B, r, fixed_rank, t[0], t[1], t[2], t[3], t[4]);
     }
     return rc;
 }

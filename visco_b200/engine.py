@@ -70,6 +70,11 @@ class Engine:
         self.lib.vk_last_stage_ms(self.h, t)
         return dict(zip(("gram", "jacobi", "select", "factors", "small", "total"), [float(x) for x in t]))
 
+    def last_eig_ms(self):
+        t = (C.c_float * 5)()
+        self.lib.vk_last_eig_ms(self.h, t)
+        return dict(zip(("tridiag", "leading_pairs", "ql", "reflectors", "rotations"), [float(x) for x in t]))
+
     def uses_small_path(self, m, n) -> bool:
         return bool(self.lib.vk_uses_small_path(int(m), int(n)))
 
