@@ -622,29 +622,33 @@ constexpr int TK_MAXK = 32;
 constexpr float TK_GAP = 0.f;  // eigenvalue-gap pre-test (relative to lambda_max); 0: rely on the duplicate test
 
 __device__ __forceinline__ int sturm_count(const float* d, const float* e2, int r, float x, float pivmin) {
-    // number of eigenvalues of T smaller than x
+    // number of eigenvalues of T smaller than x (fast division: only the signs of the pivots matter)
     int c = 0;
     float q = d[0] - x;
     if (fabsf(q) < pivmin) q = -pivmin;
     c += q < 0.f;
     for (int i = 1; i < r; ++i) {
-        q = d[i] - x - e2[i - 1] / q;
+        q = d[i] - x - __fdividef(e2[i - 1], q);
         if (fabsf(q) < pivmin) q = -pivmin;
         c += q < 0.f;
     }
     return c;
 }
 
-__global__ void __launch_bounds__(64) bisect_kernel(int r, int nev, const float* __restrict__ dall,
-                                                    const float* __restrict__ eall, float* __restrict__ lamtop,
-                                                    int32_t* __restrict__ flag, float gap) {
+// eight lanes per eigenvalue: every round evaluates seven interior points of the bracket (three bits per round)
+constexpr int BS_ROUNDS = 10;
+
+__global__ void __launch_bounds__(8 * (TK_MAXK + 1) + 24) bisect_kernel(int r, int nev, const float* __restrict__ dall,
+                                                                      const float* __restrict__ eall,
+                                                                      float* __restrict__ lamtop,
+                                                                      int32_t* __restrict__ flag, float gap) {
     extern __shared__ float bs_sm[];
     float* d = bs_sm;
     float* e2 = bs_sm + r;
-    __shared__ float s_lo[2], s_hi[2], s_lam[TK_MAXK + 1];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    __shared__ float s_lo[9], s_hi[9], s_lam[TK_MAXK + 1];
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     float lo = 3.4e38f, hi = -3.4e38f;
-    for (int i = tid; i < r; i += 64) {
+    for (int i = tid; i < r; i += nthr) {
         const float di = dall[(size_t)b * r + i];
         const float ei = i < r - 1 ? eall[(size_t)b * r + i] : 0.f;
         const float ep = i > 0 ? eall[(size_t)b * r + i - 1] : 0.f;
@@ -656,25 +660,29 @@ __global__ void __launch_bounds__(64) bisect_kernel(int r, int nev, const float*
     }
     lo = -warp_max(-lo);
     hi = warp_max(hi);
-    if ((tid & 31) == 0) s_lo[tid >> 5] = lo, s_hi[tid >> 5] = hi;
+    if (lane == 0) s_lo[tid >> 5] = lo, s_hi[tid >> 5] = hi;
     __syncthreads();
-    lo = fminf(s_lo[0], s_lo[1]);
-    hi = fmaxf(s_hi[0], s_hi[1]);
+    for (int w = 0; w < (nthr + 31) / 32; ++w) lo = fminf(lo, s_lo[w]), hi = fmaxf(hi, s_hi[w]);
     const float scale = fmaxf(fabsf(lo), fabsf(hi));
     const float pivmin = fmaxf(1e-30f, 1e-14f * scale * scale);
-    if (tid < nev) {
-        // eigenvalue number idx in ascending order: the smallest x with count(x) > idx
-        const int idx = r - 1 - tid;
-        float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
-        for (int it = 0; it < 48; ++it) {
-            const float mid = 0.5f * (a + c);
-            if (!(mid > a && mid < c)) break;
-            if (sturm_count(d, e2, r, mid, pivmin) > idx) c = mid;
-            else a = mid;
-        }
+    // eigenvalue number idx in ascending order: the smallest x with count(x) > idx
+    const int g = tid >> 3, j = tid & 7;
+    const int idx = r - 1 - g;
+    float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+    for (int it = 0; it < BS_ROUNDS; ++it) {
+        const float h = 0.125f * (c - a);
+        bool above = true;  // lane 7 stands for the upper end of the bracket
+        if (g < nev && j < 7) above = sturm_count(d, e2, r, a + (float)(j + 1) * h, pivmin) > idx;
+        const unsigned bits = (__ballot_sync(0xffffffffu, above) >> (lane & 24)) & 0xffu;
+        const int js = __ffs(bits | 0x80u) - 1;
+        const float a0 = a;
+        a = a0 + (float)js * h;
+        c = js == 7 ? c : a0 + (float)(js + 1) * h;
+    }
+    if (g < nev && j == 0) {
         const float lam = 0.5f * (a + c);
-        s_lam[tid] = lam;
-        lamtop[(size_t)b * (TK_MAXK + 1) + tid] = lam;
+        s_lam[g] = lam;
+        lamtop[(size_t)b * (TK_MAXK + 1) + g] = lam;
     }
     __syncthreads();
     if (tid == 0) {
@@ -994,7 +1002,8 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         float* lamtop = reinterpret_cast<float*>(sc + L.lamtop);
         int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
         const char* genv = getenv("VK_TK_GAP");
-        bisect_kernel<<<B, 64, (size_t)2 * r * 4, st>>>(r, k + 1, d, e, lamtop, flag, genv ? (float)atof(genv) : TK_GAP);
+        bisect_kernel<<<B, (8 * (k + 1) + 31) / 32 * 32, (size_t)2 * r * 4, st>>>(r, k + 1, d, e, lamtop, flag,
+                                                                                genv ? (float)atof(genv) : TK_GAP);
         VK_LAUNCH_CHECK(h);
         twisted_kernel<<<B, 32, 0, st>>>(r, k, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
                                          reinterpret_cast<float*>(sc + L.dm));
