@@ -450,3 +450,21 @@ def test_multiple_and_clustered_leading_singular_values(eng, k):
         err = np.linalg.norm(A.astype(np.complex128) - rec)
         assert abs(err - optimal) <= 1e-5 * optimal + 5e-6 * np.linalg.norm(A), (sv[:5], err, optimal)
         assert np.abs(U.conj().T @ U - np.eye(k)).max() < 1e-4
+
+
+@pytest.mark.parametrize("B,m,n,kw", [
+    (2, 1024, 1100, dict(compressionrank=16)),   # largest size of the direct eigensolver, leading-pair path (16 vectors)
+    (2, 1024, 1100, dict(decorrelation=0.9)),    # ... full QL path
+    (2, 700, 2000, dict(compressionrank=40)),    # fixed rank above the leading-pair limit: full path
+    (1, 1100, 1200, dict(compressionrank=8)),    # min(m, n) > 1024: cyclic Jacobi solver
+    (2, 1500, 130, dict(decorrelation=0.95)),    # tall, Gram on the column side
+])
+def test_gram_path_size_limits_of_the_eigensolvers(eng, torch, B, m, n, kw):
+    A = _device_cube(eng, torch, B, 1, m, n)
+    U, S, Vt, ranks, stats = eng.compress(A, **kw)
+    torch.cuda.synchronize()
+    Ah, Uh, Sh, Vh, rk, st = (x.cpu().numpy() for x in (A, U, S, Vt, ranks, stats))
+    assert np.all(st[:, 3] == 1)
+    for b in range(B):
+        k = int(rk[b])
+        parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"{m}x{n} {kw}", **kw)
