@@ -468,3 +468,20 @@ def test_gram_path_size_limits_of_the_eigensolvers(eng, torch, B, m, n, kw):
     for b in range(B):
         k = int(rk[b])
         parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"{m}x{n} {kw}", **kw)
+
+
+def test_direct_solver_hands_unconverged_passes_to_jacobi(eng, torch):
+    """The QL iteration is limited per eigenvalue like LAPACK's; a matrix that hits the limit sends its pass back
+    through the cyclic Jacobi solver. Forced here with a limit of one iteration."""
+    A = _device_cube(eng, torch, 2, 4, 160, 320)
+    base = eng.compress(A, decorrelation=0.95)
+    assert float(base[4][:, 2].min()) > 100          # QL iterations: the direct solver ran
+    try:
+        eng.set_option("ql_maxit", 1)
+        got = eng.compress(A, decorrelation=0.95)
+    finally:
+        eng.set_option("ql_maxit", 60)
+    torch.cuda.synchronize()
+    assert float(got[4][:, 3].min()) == 1 and float(got[4][:, 2].max()) <= 30   # converged, in Jacobi sweeps
+    assert torch.equal(got[3], base[3])
+    assert float(((got[1] - base[1]).abs() / base[1].clamp_min(1e-20)).max()) < 1e-4

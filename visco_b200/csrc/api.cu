@@ -137,7 +137,7 @@ int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, f
 
 int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
                    float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L,
-                   int sub0 = 0, bool gram_done = false) {
+                   int sub0 = 0, bool gram_done = false, bool force_jacobi = false) {
     // sub0: index of this chunk's first matrix inside the Gram super-chunk (W and gscale are laid out per super-chunk)
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
@@ -176,7 +176,8 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         if (!gram_done && (rc = gram_stage(h, A, B, m, n, W, gscale, nonfinite))) return rc;
         tm.mark(1);
         // fixed small rank: blocked subspace iteration first; the full Jacobi solver only sees what it left unsolved
-        if (use_qr(h, m, n, fixed_rank)) {
+        const bool qr = use_qr(h, m, n, fixed_rank) && !force_jacobi;
+        if (qr) {
             if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done, fixed_rank))) return rc;
         } else {
             const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
@@ -197,11 +198,23 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         tm.collect(2, 2, 3);
         tm.collect(3, 3, 4);
     }
-    // poll: non-finite input / non-convergence (one 8-byte copy; the Jacobi loop has usually synchronised already)
-    if (h->check_finite) {
+    // poll: non-finite input, and whether the direct eigensolver gave a matrix up (QL iteration limit, rotation store)
+    const bool qr_used = !small_path(m, n) && use_qr(h, m, n, fixed_rank) && !force_jacobi;
+    if (h->check_finite || qr_used) {
+        h->h_poll[2] = 0;
+        if (qr_used) {
+            if ((rc = vk_launch_count_not_done(h, done, B, active))) return rc;
+            VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 2, active, 4, cudaMemcpyDeviceToHost, h->stream));
+        }
         VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 1, nonfinite, 4, cudaMemcpyDeviceToHost, h->stream));
         VK_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (h->h_poll[1]) return vk_fail(h, VK_ENONFINITE, "input contains NaN or Inf");
+        if (h->check_finite && h->h_poll[1]) return vk_fail(h, VK_ENONFINITE, "input contains NaN or Inf");
+        if (h->h_poll[2] > 0) {
+            // rare: redo this pass with the cyclic Jacobi solver (the Gram matrices were overwritten: recompute them)
+            h->eig_fallbacks++;
+            return compress_chunk(h, A, B, m, n, fixed_rank, decorrelation, kmax, U, S, Vt, ranks, stats, ws, L, sub0, false,
+                                  true);
+        }
     }
     return VK_OK;
 }
@@ -320,6 +333,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_generic = (int)v;
     else if (k == "eig_impl")
         h->eig_impl = (int)v;
+    else if (k == "ql_maxit")
+        h->ql_maxit = (int)v;
     else if (k == "chunk")
         h->chunk = (int)v;
     else

@@ -43,6 +43,8 @@ struct vk_context {
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
+    int ql_maxit = 60;       // QL iterations allowed per eigenvalue (tests lower it to exercise the Jacobi fallback)
+    int64_t eig_fallbacks = 0;  // internal passes the direct solver handed back to the Jacobi solver
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     float eig_ms[5] = {0, 0, 0, 0, 0};  // direct eigensolver: tridiag, leading pairs, QL, reflector accumulation, rotations
     cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -131,6 +133,7 @@ int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int
                      float* S_dev, int32_t* ranks_dev, float* stats_dev, const int32_t* sweeps_dev,
                      const int32_t* done_dev);
 int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info);
+int vk_launch_count_not_done(vk_context* h, const int32_t* done, int B, int32_t* out);
 int vk_launch_find_n(vk_context* h, const float* S, int B, int r, double decorrelation, int32_t* ranks);
 
 // factor formation

@@ -716,6 +716,27 @@ int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int
     return VK_OK;
 }
 
+// out[0] = number of matrices whose eigensolver reported failure (done == 0)
+__global__ void count_not_done_kernel(const int32_t* __restrict__ done, int B, int32_t* __restrict__ out) {
+    int c = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) c += done[b] == 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        out[0] = t;
+    }
+}
+
+int vk_launch_count_not_done(vk_context* h, const int32_t* done, int B, int32_t* out) {
+    count_not_done_kernel<<<1, 256, 0, h->stream>>>(done, B, out);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info) {
     pack_info_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(sweeps, done, B, info);
     VK_LAUNCH_CHECK(h);

@@ -341,7 +341,7 @@ struct SweepRec {
 __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict__ dall, const float* __restrict__ eall,
                                                  float* __restrict__ lamall, float2* __restrict__ csall,
                                                  SweepRec* __restrict__ swall, int32_t* __restrict__ metaall, int cap,
-                                                 int scap, int lcap, const int32_t* __restrict__ skip) {
+                                                 int scap, int lcap, const int32_t* __restrict__ skip, int maxit) {
     extern __shared__ float ql_sm[];
     float2* de = reinterpret_cast<float2*>(ql_sm) + 1;  // de[i] = (d_i, e_i), i = -1 .. r-1 (de[-1] is a pad)
     int* endlv = reinterpret_cast<int*>(ql_sm + 2 * (r + 2));  // [RA_NS] end level of the last sweep of each slot
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict_
                 }
             }
             if (m == l) break;
-            if (++it > QL_MAXIT) {
+            if (++it > maxit) {
                 status = 2;
                 break;
             }
@@ -1024,7 +1024,8 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         VK_CUDA(h, cudaFuncSetAttribute(tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tql_kernel<<<B, 32, smem, st>>>(r, d, e, reinterpret_cast<float*>(sc + L.lam),
                                         reinterpret_cast<float2*>(sc + L.cs), reinterpret_cast<SweepRec*>(sc + L.sw),
-                                        reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap, skip);
+                                        reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap, skip,
+                                        h->ql_maxit > 0 ? h->ql_maxit : QL_MAXIT);
         VK_LAUNCH_CHECK(h);
     }
     if (dbg) cudaEventRecord(ev[3], st);
