@@ -340,8 +340,11 @@ def run_ours(args):
         tri = {"bound": "hbm", "kernel": "tridiag_kernel (Householder tridiagonalisation, fused rank-2 update + matvec)",
                "achieved": tb / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                "frac": tb / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if t_ms > 0 else None,
-               "traffic": {"kat7": 194.4e6}.get(args.workload),
-               "traffic_source": "profiles/r01_ncu_full_tridiag_kat7.txt" if args.workload == "kat7" else None,
+               # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full): the KAT-7 cube as captured;
+               # MeerKAT: 181.2 GB for a 296-matrix launch, scaled to the matrices of this launch
+               "traffic": {"kat7": 194.4e6, "meerkat": 181.2e9 / 296 * min(B, eig_chunk)}.get(args.workload),
+               "traffic_source": {"kat7": "profiles/r01_ncu_full_tridiag_kat7.txt",
+                                  "meerkat": "profiles/r01_ncu_full_tridiag_r512.txt"}.get(args.workload),
                "avg_launch_ms": t_ms / max(1.0, math.ceil(B / max(1, eig_chunk))), "ms": t_ms,
                "launches_per_step": float(max(1, math.ceil(B / max(1, eig_chunk)))),
                "share_of_step": t_ms / ms_per_step if ms_per_step else None,
