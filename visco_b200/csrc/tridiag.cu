@@ -11,7 +11,6 @@
 // Xt holds (Q D Z)^T: row i is eigenvector i, so a plane rotation of columns (i, i+1) of Z acts on rows i, i+1 of Xt.
 // On exit W[b][i][:] = lambda_i * conj(Xt[i][:]) - the layout the Jacobi solver leaves (vectors of norm lambda_i).
 #include <cstdio>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -1001,9 +1000,8 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         const int k = fixed_rank;
         float* lamtop = reinterpret_cast<float*>(sc + L.lamtop);
         int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
-        const char* genv = getenv("VK_TK_GAP");
         bisect_kernel<<<B, (8 * (k + 1) + 31) / 32 * 32, (size_t)2 * r * 4, st>>>(r, k + 1, d, e, lamtop, flag,
-                                                                                genv ? (float)atof(genv) : TK_GAP);
+                                                                                TK_GAP);
         VK_LAUNCH_CHECK(h);
         twisted_kernel<<<B, 32, 0, st>>>(r, k, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
                                          reinterpret_cast<float*>(sc + L.dm));
