@@ -160,3 +160,41 @@ def test_flag_kernels_and_flag_replacement_end_to_end(tmp_path):
         # full rank (16 channels): the decompressed column equals the flag-replaced input, not the dirty one
         for c in (0, 3):
             np.testing.assert_allclose(out.data[:, :, c], clean[:, :, c].astype(np.complex64), atol=2e-4 * np.abs(clean).max())
+
+
+def test_weight_spectrum_rank1_and_the_reference_decompression_quirk(tmp_path):
+    """WEIGHT_SPECTRUM[:, :, 0] is stored as its leading singular triplet (compress_ms.py:489-503) in
+    float32, with dask's svd_flip sign; decompression returns U.diag(S) only, tiled over the correlations, for both
+    WEIGHT_SPECTRUM and SIGMA_SPECTRUM (decompress_ms.py:248-270)."""
+    import json
+
+    from visco_b200.compress_ms import compress_full_ms, weight_spectrum_rank1
+    from visco_b200.decompress_ms import open_dataset
+    from visco_b200.zarr_leaf import read_svd_from_zarr
+    vis = VisData.load(BUNDLE)
+    nrow, nchan, ncorr = vis.data.shape
+    rng = np.random.default_rng(7)
+    ws = (1.0 + rng.random((nrow, 1, 1))) * (0.5 + rng.random((1, nchan, 1))) * (1 + 0.05 * rng.random((nrow, nchan, ncorr)))
+    vis.weight_spectrum = ws.astype(np.float32)
+    bundle = str(tmp_path / "with_weights.npz")
+    vis.save(bundle)
+    assert VisData.load(bundle).weight_spectrum.shape == (nrow, nchan, ncorr)
+    store = str(tmp_path / "w.zarr")
+    compress_full_ms(bundle, store, correlation="XX,YY", compressionrank=2, **KW)
+    leaf = os.path.join(store, "WEIGHT_SPECTRUM")
+    assert json.load(open(os.path.join(leaf, "U", ".zarray")))["dtype"] == "<f4"       # real factors stay real
+    U, S, WT, rowid = read_svd_from_zarr(leaf)
+    assert U.shape == (nrow, 1) and S.shape == (1,) and WT.shape == (1, nchan)
+    np.testing.assert_array_equal(rowid, vis.rowid)
+    u, s, vt = vo.ref_apply_svd(vis.weight_spectrum[:, :, 0], compressionrank=1)        # the reference, float32 LAPACK
+    np.testing.assert_allclose(S, s, rtol=1e-4)
+    np.testing.assert_allclose(U.real, u, atol=2e-5 * np.abs(u).max())                  # same sign convention
+    np.testing.assert_allclose(WT.real, vt, atol=2e-5 * np.abs(vt).max())
+    assert not U.imag.any() and not WT.imag.any()
+    u1, s1, v1 = weight_spectrum_rank1(vis.weight_spectrum)
+    assert u1.dtype == np.float32 and v1.dtype == np.float32 and v1.sum() >= 0
+    out = open_dataset(store)
+    ref = np.tile(np.expand_dims(np.dot(u, np.diag(s)), axis=-1), (1, 1, ncorr))        # decompress_ms.py:252-254
+    assert out.weight_spectrum.shape == (nrow, 1, ncorr)
+    np.testing.assert_allclose(out.weight_spectrum, ref, rtol=1e-4, atol=1e-6)
+    assert out.sigma_spectrum is out.weight_spectrum or np.array_equal(out.sigma_spectrum, out.weight_spectrum)

@@ -118,3 +118,29 @@ def test_writer_rejects_inconsistent_factors(tmp_path):
         zl.write_svd_to_zarr((U, S, V), tmp_path / "y", None, 1, np.arange(35))
     with pytest.raises(FileNotFoundError):
         zl.read_svd_from_zarr(tmp_path / "nothing")
+
+
+def test_real_factors_are_stored_as_float32_and_bundle_keeps_weights(tmp_path):
+    """The rank-1 WEIGHT_SPECTRUM leaf of the reference holds real float32 factors (compress_ms.py:493-498)."""
+    import json
+
+    from visco_b200.msdata import VisData
+    from visco_b200.zarr_leaf import read_svd_from_zarr, write_svd_to_zarr
+    rng = np.random.default_rng(0)
+    u = rng.random((12, 1)).astype(np.float32)
+    s = np.array([3.0], np.float32)
+    v = rng.random((1, 5)).astype(np.float32)
+    write_svd_to_zarr((u, s, v), tmp_path / "WEIGHT_SPECTRUM", "zstd", 3, np.arange(12))
+    assert json.load(open(tmp_path / "WEIGHT_SPECTRUM" / "U" / ".zarray"))["dtype"] == "<f4"
+    assert json.load(open(tmp_path / "WEIGHT_SPECTRUM" / "WT" / ".zarray"))["dtype"] == "<f4"
+    U, S, WT, rowid = read_svd_from_zarr(tmp_path / "WEIGHT_SPECTRUM")
+    np.testing.assert_array_equal(U.real, u)
+    np.testing.assert_array_equal(WT.real, v)
+    vis = VisData(data=np.zeros((6, 3, 4), np.complex64), antenna1=[0] * 6, antenna2=[1] * 6, antenna_names=["a", "b"],
+                  weight_spectrum=rng.random((6, 3, 4)))
+    vis.save(str(tmp_path / "b.npz"))
+    back = VisData.load(str(tmp_path / "b.npz"))
+    assert back.weight_spectrum.dtype == np.float32 and back.weight_spectrum.shape == (6, 3, 4)
+    with pytest.raises(ValueError):
+        VisData(data=np.zeros((6, 3, 4), np.complex64), antenna1=[0] * 6, antenna2=[1] * 6, antenna_names=["a", "b"],
+                weight_spectrum=np.zeros((5, 3, 4)))

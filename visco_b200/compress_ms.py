@@ -66,6 +66,24 @@ def apply_svd_batched(cube, decorrelation: float = None, compressionrank: int = 
 # per-(baseline, correlation) gather, leaf tree. Mirrors reference compress_ms.py:366-703 with the per-matrix dask
 # tasks replaced by ONE apply_svd_batched call per batch of baselines.
 # =====================================================================================================================
+def weight_spectrum_rank1(weight_spectrum):
+    """Leading singular triplet of WEIGHT_SPECTRUM[:, :, 0] (reference compress_ms.py:493-494:
+    ``apply_svd(ws, compressionrank=1)`` on the real nrow x nchan plane). The device path works in complex64; for a real
+    matrix the leading pair is real up to one unit phase, which is removed here, and the sign follows dask's svd_flip
+    (sum of the right vector >= 0) as the reference's factors do. Returns float32 (U[nrow, 1], S[1], Vt[1, nchan])."""
+    ws = np.asarray(weight_spectrum)
+    if ws.ndim == 3:
+        ws = ws[:, :, 0]
+    U, S, Vt = apply_svd(np.ascontiguousarray(ws, dtype=np.complex64), compressionrank=1)
+    i = int(np.argmax(np.abs(U[:, 0])))
+    ph = U[i, 0] / abs(U[i, 0]) if abs(U[i, 0]) > 0 else 1.0
+    u = (U[:, 0] * np.conj(ph)).real.astype(np.float32)
+    v = (Vt[0] * ph).real.astype(np.float32)
+    if v.sum() < 0:
+        u, v = -u, -v
+    return u[:, None], S.astype(np.float32), v[None, :]
+
+
 def batch_baselines(baselines, batch_size):
     """Split the baseline list into batches of `batch_size` (reference compress_ms.py:366-386)."""
     batch_size = max(1, int(batch_size))
@@ -215,6 +233,11 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
     for group, packed in (("FLAGS", eng.packbits(flag_dev)), ("FLAGS_ROW", eng.packbits(torch.from_numpy(flag_row).to(dev)))):
         p = packed.cpu().numpy()
         write_group(os.path.join(zarr_path, group), {group: (p, ("row",)), "row": (np.arange(p.shape[0]), ("row",))})
+    # WEIGHT_SPECTRUM: first correlation plane, rank 1, at the leaf <store>/WEIGHT_SPECTRUM (reference :486-503)
+    if vis.weight_spectrum is not None:
+        from .zarr_leaf import write_svd_to_zarr
+        write_svd_to_zarr(weight_spectrum_rank1(vis.weight_spectrum), os.path.join(zarr_path, "WEIGHT_SPECTRUM"),
+                          compressor, level, vis.rowid)
     # flagged-value replacement before the SVD (reference :530-566)
     if use_model_data:
         mod = vis.model_data

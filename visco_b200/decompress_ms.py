@@ -171,8 +171,16 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         packed = torch.from_numpy(read_array(os.path.join(zarr_path, "FLAGS_ROW", "FLAGS_ROW")).astype(np.uint8)).to(dev)
         flag_row = eng.unpackbits(packed, out.shape[0]).cpu().numpy().astype(bool)
     corr_types = [9, 10, 11, 12][:ncorr] if ncorr <= 4 else list(range(ncorr))
+    # WEIGHT_SPECTRUM / SIGMA_SPECTRUM: the reference multiplies U by diag(S) ONLY (decompress_ms.py:252-254: no WT),
+    # expands a trailing axis and tiles it over the correlations, i.e. the columns come back as (row, 1, corr) with the
+    # row profile of the weights and no channel dependence; both columns get the same array (:257-270). Kept as is.
+    weights = None
+    if os.path.isdir(os.path.join(zarr_path, "WEIGHT_SPECTRUM", "U")):
+        Uw, Sw, _, _ = read_svd_from_zarr(os.path.join(zarr_path, "WEIGHT_SPECTRUM"))
+        wrec = np.dot(Uw.real.astype(np.float32), np.diag(Sw))
+        weights = np.tile(np.expand_dims(wrec, axis=-1), (1, 1, ncorr))
     return VisData(data=out, antenna1=ant1, antenna2=ant2, antenna_names=antnames, corr_types=corr_types, rowid=rowid,
-                   flag=flag, flag_row=flag_row)
+                   flag=flag, flag_row=flag_row, weight_spectrum=weights, sigma_spectrum=weights)
 
 
 def open_dataset(zarr_path: str, column: str = "COMPRESSED_DATA", batch_size: int = 50):

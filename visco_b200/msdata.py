@@ -33,6 +33,8 @@ class VisData:
     flag: np.ndarray | None = None   # [row, chan, corr] bool (optional)
     flag_row: np.ndarray | None = None       # [row] bool (optional)
     model_data: np.ndarray | None = None     # [row, chan, corr] complex64 (optional; flag replacement source)
+    weight_spectrum: np.ndarray | None = None  # [row, chan, corr] float32 (optional; compressed to rank 1)
+    sigma_spectrum: np.ndarray | None = None   # only set by the decompressor (reference decompress_ms.py:263-269)
     column: str = "DATA"
 
     def __post_init__(self):
@@ -61,6 +63,10 @@ class VisData:
             self.model_data = np.ascontiguousarray(self.model_data, dtype=np.complex64)
             if self.model_data.shape != self.data.shape:
                 raise ValueError("MODEL_DATA must have the shape of the visibility column")
+        if self.weight_spectrum is not None:
+            self.weight_spectrum = np.ascontiguousarray(self.weight_spectrum, dtype=np.float32)
+            if self.weight_spectrum.ndim != 3 or self.weight_spectrum.shape[0] != nrow:
+                raise ValueError("WEIGHT_SPECTRUM must be [row, chan, corr]")
 
     # --------------------------------------------------------------------------------------------- persistence
     def save(self, path: str):
@@ -68,7 +74,9 @@ class VisData:
                             ANTENNA_NAME=np.array(self.antenna_names), CORR_TYPE=np.array(self.corr_types, np.int32),
                             **({"FLAG": self.flag} if self.flag is not None else {}),
                             **({"FLAG_ROW": self.flag_row} if self.flag_row is not None else {}),
-                            **({"MODEL_DATA": self.model_data} if self.model_data is not None else {}))
+                            **({"MODEL_DATA": self.model_data} if self.model_data is not None else {}),
+                            **({"WEIGHT_SPECTRUM": self.weight_spectrum} if self.weight_spectrum is not None else {}),
+                            **({"SIGMA_SPECTRUM": self.sigma_spectrum} if self.sigma_spectrum is not None else {}))
 
     @classmethod
     def load(cls, path: str, column: str = "DATA", scan=None, fieldid=None, ddid=None):
@@ -82,7 +90,8 @@ class VisData:
                            antenna_names=list(z["ANTENNA_NAME"]), corr_types=list(z["CORR_TYPE"]), rowid=z["ROWID"],
                            flag=z["FLAG"] if "FLAG" in z.files else None,
                            flag_row=z["FLAG_ROW"] if "FLAG_ROW" in z.files else None,
-                           model_data=z["MODEL_DATA"] if "MODEL_DATA" in z.files else None, column=column)
+                           model_data=z["MODEL_DATA"] if "MODEL_DATA" in z.files else None,
+                           weight_spectrum=z["WEIGHT_SPECTRUM"] if "WEIGHT_SPECTRUM" in z.files else None, column=column)
         if not os.path.exists(path):
             raise ValueError(f"Measurement Set {path} does not exist")     # reference compress_ms.py:876-877
         try:
@@ -106,7 +115,8 @@ class VisData:
         names = list(table(os.path.join(path, "ANTENNA"), ack=False).getcol("NAME"))
         corr = list(table(os.path.join(path, "POLARIZATION"), ack=False).getcol("CORR_TYPE")[0])
         return cls(data=t.getcol(column), antenna1=t.getcol("ANTENNA1"), antenna2=t.getcol("ANTENNA2"), antenna_names=names,
-                   corr_types=corr, rowid=np.asarray(t.rownumbers(), dtype=np.int64), column=column)
+                   corr_types=corr, rowid=np.asarray(t.rownumbers(), dtype=np.int64), column=column,
+                   weight_spectrum=t.getcol("WEIGHT_SPECTRUM") if "WEIGHT_SPECTRUM" in t.colnames() else None)
 
     # --------------------------------------------------------------------------------------------- hot-path helpers
     def baselines(self, antennas=None):

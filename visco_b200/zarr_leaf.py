@@ -250,9 +250,11 @@ def write_svd_to_zarr(svd_result, path, compressor: str, level: int, rowid: np.n
     store rooted AT THE LEAF with U(time, mode), S(mode), WT(mode, channel) + coordinates time/mode/channel; the data
     variables use the requested compressor, the coordinates none."""
     U, s, V = svd_result
-    U = np.ascontiguousarray(np.asarray(U), dtype=np.complex64)
+    # real factors (the rank-1 WEIGHT_SPECTRUM leaf, compress_ms.py:493-498) stay float32 as in the reference
+    vdt = np.float32 if (np.isrealobj(np.asarray(U)) and np.isrealobj(np.asarray(V))) else np.complex64
+    U = np.ascontiguousarray(np.asarray(U), dtype=vdt)
     s = np.ascontiguousarray(np.asarray(s), dtype=np.float32)
-    V = np.ascontiguousarray(np.asarray(V), dtype=np.complex64)
+    V = np.ascontiguousarray(np.asarray(V), dtype=vdt)
     if U.ndim != 2 or V.ndim != 2 or s.ndim != 1 or U.shape[1] != s.shape[0] or V.shape[0] != s.shape[0]:
         raise ValueError(f"inconsistent factor shapes U{U.shape} S{s.shape} WT{V.shape}")
     rowid = np.asarray(rowid)
