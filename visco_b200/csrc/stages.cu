@@ -48,9 +48,9 @@ struct GramOp1 {  // W[i][j] = sum_t A[t][i] * conj(A[t][j])          (r = n)
 };
 
 // scale W[b] so that trace == r; gscale[b] = trace / r. One CTA per matrix.
-__global__ void __launch_bounds__(256) gram_normalise_kernel(float2* __restrict__ W, int r, float* __restrict__ gscale,
+__global__ void __launch_bounds__(1024) gram_normalise_kernel(float2* __restrict__ W, int r, float* __restrict__ gscale,
                                                              int32_t* __restrict__ nonfinite) {
-    __shared__ float part[8];
+    __shared__ float part[32];
     __shared__ float sc;
     const int b = blockIdx.x;
     float2* Wb = W + (size_t)b * r * r;
@@ -74,11 +74,22 @@ __global__ void __launch_bounds__(256) gram_normalise_kernel(float2* __restrict_
     __syncthreads();
     const float f = sc;
     const size_t tot = (size_t)r * r;
-    for (size_t e = threadIdx.x; e < tot; e += blockDim.x) {
-        float2 v = Wb[e];
-        v.x *= f;
-        v.y *= f;
-        Wb[e] = v;
+    if ((tot & 1) == 0) {  // two complex numbers per access (the matrix base is 16-byte aligned when r*r is even)
+        float4* W4 = reinterpret_cast<float4*>(Wb);
+        const size_t n4 = tot >> 1;
+#pragma unroll 4
+        for (size_t e = threadIdx.x; e < n4; e += blockDim.x) {
+            float4 v = W4[e];
+            v.x *= f, v.y *= f, v.z *= f, v.w *= f;
+            W4[e] = v;
+        }
+    } else {
+        for (size_t e = threadIdx.x; e < tot; e += blockDim.x) {
+            float2 v = Wb[e];
+            v.x *= f;
+            v.y *= f;
+            Wb[e] = v;
+        }
     }
 }
 
@@ -691,7 +702,7 @@ int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int
 }
 
 int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev) {
-    gram_normalise_kernel<<<B, 256, 0, h->stream>>>(W, r, gscale_dev, nonfinite_dev);
+    gram_normalise_kernel<<<B, r >= 128 ? 1024 : 256, 0, h->stream>>>(W, r, gscale_dev, nonfinite_dev);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }

@@ -10,6 +10,7 @@
 //   T = D T_real D^H with unit phases D, T_real = Z Lambda Z^T  =>  eigenvectors of M are the columns of Q D Z.
 // Xt holds (Q D Z)^T: row i is eigenvector i, so a plane rotation of columns (i, i+1) of Z acts on rows i, i+1 of Xt.
 // On exit W[b][i][:] = lambda_i * conj(Xt[i][:]) - the layout the Jacobi solver leaves (vectors of norm lambda_i).
+#include <cmath>
 #include <cstdio>
 
 #include "common.cuh"
@@ -53,9 +54,11 @@ __device__ __forceinline__ float2 block_sum2(float2 v, float2* scratch) {
 template <int EPL, int RB>
 __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
     tridiag_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
-                   float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall) {
+                   float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
     constexpr int WD = EPL * 32;
     extern __shared__ float2 td_sm[];
+    float2* T = td_sm + 5 * WD;  // [ts][ts] trailing block once it fits (ts <= nts): rows/cols j0 .. r-1
+    int j0 = -1, ts = 0;         // j0 >= 0: resident
     float2* vprev = td_sm;
     float2* vnew = td_sm + WD;
     float2* wv = td_sm + 2 * WD;
@@ -76,6 +79,15 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
 
     for (int j = 0; j + 2 < r; ++j) {
         const int e0 = (j + 1) >> 5;
+        if (j0 < 0 && r - j <= nts) {
+            // from here on the trailing block lives in shared memory: the remaining steps never wait for L2 again
+            j0 = j, ts = r - j;
+            for (int idx = tid; idx < ts * ts; idx += TD_THREADS) {
+                const int i = idx / ts, k = idx - i * ts;
+                T[idx] = M[(size_t)(j0 + i) * ld + j0 + k];
+            }
+            __syncthreads();
+        }
         // row j with the pending update of step j-1 applied: diagonal d_j and the column below it (a = conj(row))
         float ss = 0.f;
         {
@@ -124,6 +136,26 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
             for (int k = j + 1 + tid; k < r; k += TD_THREADS) row[k] = vnew[k];
         }
         // fused pass over the trailing block
+        if (j0 >= 0) {
+            for (int i = j + 1 + warp; i < r; i += TD_WARPS) {
+                float2* row = T + (size_t)(i - j0) * ts - j0;
+                const float2 vi = vprev[i], wi = wv[i];
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+                for (int k = j + 1 + lane; k < r; k += 32) {
+                    float2 t = row[k];
+                    const float2 wk = wv[k], vk = vprev[k];
+                    t.x -= vi.x * wk.x + vi.y * wk.y + wi.x * vk.x + wi.y * vk.y;
+                    t.y -= vi.y * wk.x - vi.x * wk.y + wi.y * vk.x - wi.x * vk.y;
+                    row[k] = t;
+                    if (i == j + 1) nrow[k] = t;
+                    cfma(acc, t, vnew[k]);
+                }
+                acc.x = warp_sum(acc.x);
+                acc.y = warp_sum(acc.y);
+                if (lane == 0) pv[i] = make_float2(tau * acc.x, tau * acc.y);
+            }
+        } else
         for (int ib = j + 1 + warp; ib < r; ib += TD_WARPS * RB) {
             float2 x[RB][EPL];
 #pragma unroll
@@ -207,7 +239,13 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
             d[0] = M[0].x;
         } else {
             const int j = r - 2;
-            float2 x00 = M[(size_t)j * ld + j], x01 = M[(size_t)j * ld + j + 1], x11 = M[(size_t)(j + 1) * ld + j + 1];
+            float2 x00, x01, x11;
+            if (j0 >= 0) {
+                x00 = T[(size_t)(j - j0) * ts + j - j0], x01 = T[(size_t)(j - j0) * ts + j + 1 - j0];
+                x11 = T[(size_t)(j + 1 - j0) * ts + j + 1 - j0];
+            } else {
+                x00 = M[(size_t)j * ld + j], x01 = M[(size_t)j * ld + j + 1], x11 = M[(size_t)(j + 1) * ld + j + 1];
+            }
             if (r >= 3) {
                 const float2 v0 = vprev[j], v1 = vprev[j + 1], w0 = wv[j], w1 = wv[j + 1];
                 x00.x -= 2.f * (v0.x * w0.x + v0.y * w0.y);
@@ -907,9 +945,16 @@ EigScratch eig_layout(int B, int r) {
 template <int EPL, int RB>
 int launch_tridiag(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
                    float* tau, float2* ph) {
-    const size_t smem = (size_t)5 * EPL * 32 * sizeof(float2);
+    // vectors + the largest trailing block that fits next to them (kept in shared memory for the last nts steps)
+    const size_t vec = (size_t)5 * EPL * 32 * sizeof(float2);
+    int nts = (int)sqrt((double)(VK_SMEM_BUDGET - vec) / sizeof(float2));
+    if (nts > r) nts = r;
+    // measured: 0.82 -> 0.69 ms at r = 160, 2.11 -> 2.04 ms at r = 256 (112 matrices); at r = 512 the 200 KB of shared
+    // memory cost the global phase its L1 (35.5 -> 40.9 ms per 296 matrices), so large matrices stay all-global
+    if (r > 384) nts = 0;
+    const size_t smem = vec + (size_t)nts * nts * sizeof(float2);
     VK_CUDA(h, cudaFuncSetAttribute(tridiag_kernel<EPL, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tridiag_kernel<EPL, RB><<<B, TD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph);
+    tridiag_kernel<EPL, RB><<<B, TD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
