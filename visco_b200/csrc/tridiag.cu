@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
     float2* wv = td_sm + 2 * WD;
     float2* pv = td_sm + 3 * WD;
     float2* nrow = td_sm + 4 * WD;  // row j+1 as the pass of step j left it (saves a global round trip per step)
-    __shared__ float2 scratch[TD_WARPS];
-    __shared__ float s_tau;
+    __shared__ float s_part[TD_WARPS];    // per-warp partial of |a|^2
+    __shared__ float2 s_kpart[TD_WARPS];  // per-warp partial of v^H p
+    __shared__ float2 s_alpha;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float2* M = Wall + (size_t)b * wstride;
     float* d = dall + (size_t)b * r;
@@ -104,38 +105,49 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
                     } else {
                         a = make_float2(x.x, -x.y);
                         ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                        if (k == j + 1) s_alpha = a;
                     }
                 }
                 vnew[k] = a;
             }
         }
-        const float2 tot = block_sum2(make_float2(ss, 0.f), scratch);
-        if (tid == 0) {
-            float tau = 0.f, ej = 0.f;
-            if (tot.x > 1e-30f) {
-                const float xn = sqrtf(tot.x);
-                const float2 alpha = vnew[j + 1];
+        // four barriers per step: every thread sums the per-warp partials and repeats the scalar work itself
+        ss = warp_sum(ss);
+        if (lane == 0) s_part[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) tot += s_part[w];
+        float tau = 0.f;
+        {
+            float ej = 0.f;
+            float2 v0 = s_alpha;
+            if (tot > 1e-30f) {
+                const float xn = sqrtf(tot);
+                const float2 alpha = v0;
                 const float aa = sqrtf(alpha.x * alpha.x + alpha.y * alpha.y);
                 float2 p1 = make_float2(1.f, 0.f);
                 if (aa > 0.f) p1 = make_float2(alpha.x / aa, alpha.y / aa);
-                vnew[j + 1] = make_float2(alpha.x + p1.x * xn, alpha.y + p1.y * xn);
+                v0 = make_float2(alpha.x + p1.x * xn, alpha.y + p1.y * xn);
                 tau = 1.f / (xn * (xn + aa));
                 ej = xn;
                 phase = cmulf(phase, make_float2(-p1.x, -p1.y));  // sub-diagonal element is -p1 * xn
             }
-            taus[j] = tau;
-            e[j] = ej;
-            ph[j + 1] = phase;
-            s_tau = tau;
+            if (tid == 0) {
+                vnew[j + 1] = v0;
+                taus[j] = tau;
+                e[j] = ej;
+                ph[j + 1] = phase;
+            }
         }
         __syncthreads();
-        const float tau = s_tau;
         // the reflector replaces the (now dead) part of row j right of the diagonal
         {
             float2* row = M + (size_t)j * ld;
             for (int k = j + 1 + tid; k < r; k += TD_THREADS) row[k] = vnew[k];
         }
         // fused pass over the trailing block
+        float2 kacc = make_float2(0.f, 0.f);  // this warp's part of v^H p (identical on all its lanes)
         if (j0 >= 0) {
             for (int i = j + 1 + warp; i < r; i += TD_WARPS) {
                 float2* row = T + (size_t)(i - j0) * ts - j0;
@@ -151,9 +163,12 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
                     if (i == j + 1) nrow[k] = t;
                     cfma(acc, t, vnew[k]);
                 }
-                acc.x = warp_sum(acc.x);
-                acc.y = warp_sum(acc.y);
-                if (lane == 0) pv[i] = make_float2(tau * acc.x, tau * acc.y);
+                acc.x = tau * warp_sum(acc.x);
+                acc.y = tau * warp_sum(acc.y);
+                const float2 v = vnew[i];
+                kacc.x += v.x * acc.x + v.y * acc.y;
+                kacc.y += v.x * acc.y - v.y * acc.x;
+                if (lane == 0) pv[i] = acc;
             }
         } else
         for (int ib = j + 1 + warp; ib < r; ib += TD_WARPS * RB) {
@@ -210,20 +225,20 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
                             if (ee >= e0 && k > j && k < r) nrow[k] = x[q][ee];
                         }
                     }
-                    const float ax = warp_sum(acc[q].x), ay = warp_sum(acc[q].y);
-                    if (lane == 0) pv[i] = make_float2(tau * ax, tau * ay);
+                    const float ax = tau * warp_sum(acc[q].x), ay = tau * warp_sum(acc[q].y);
+                    const float2 v = vnew[i];
+                    kacc.x += v.x * ax + v.y * ay;
+                    kacc.y += v.x * ay - v.y * ax;
+                    if (lane == 0) pv[i] = make_float2(ax, ay);
                 }
             }
         }
+        if (lane == 0) s_kpart[warp] = kacc;
         __syncthreads();
         // K = tau/2 * v^H p ;  w = p - K v
-        float2 part = make_float2(0.f, 0.f);
-        for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
-            const float2 v = vnew[k], p = pv[k];
-            part.x += v.x * p.x + v.y * p.y;
-            part.y += v.x * p.y - v.y * p.x;
-        }
-        const float2 kk = block_sum2(part, scratch);
+        float2 kk = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) kk.x += s_kpart[w].x, kk.y += s_kpart[w].y;
         const float2 K = make_float2(0.5f * tau * kk.x, 0.5f * tau * kk.y);
         for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
             const float2 v = vnew[k], p = pv[k];
