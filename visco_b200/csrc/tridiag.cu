@@ -23,8 +23,7 @@ constexpr int FQ_THREADS = 256;
 constexpr int FQ_WARPS = FQ_THREADS / 32;
 constexpr int FQ_TJ = 8;  // reflectors staged per shared-memory tile
 constexpr int RA_C = 8;     // columns of Xt per slab = lanes per application slot
-constexpr int RA_NS = 64;   // application slots per CTA = sweeps in flight
-constexpr int RA_THREADS = RA_C * RA_NS;
+constexpr int RA_NS_MAX = 128;  // application slots per CTA = sweeps in flight: 64 (r <= 256) or 128
 constexpr int QL_MAXIT = 60;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
@@ -393,10 +392,10 @@ struct SweepRec {
 __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict__ dall, const float* __restrict__ eall,
                                                  float* __restrict__ lamall, float2* __restrict__ csall,
                                                  SweepRec* __restrict__ swall, int32_t* __restrict__ metaall, int cap,
-                                                 int scap, int lcap, const int32_t* __restrict__ skip, int maxit) {
+                                                 int scap, int lcap, const int32_t* __restrict__ skip, int maxit, int nslots) {
     extern __shared__ float ql_sm[];
     float2* de = reinterpret_cast<float2*>(ql_sm) + 1;  // de[i] = (d_i, e_i), i = -1 .. r-1 (de[-1] is a pad)
-    int* endlv = reinterpret_cast<int*>(ql_sm + 2 * (r + 2));  // [RA_NS] end level of the last sweep of each slot
+    int* endlv = reinterpret_cast<int*>(ql_sm + 2 * (r + 2));  // [nslots] end level of the last sweep of each slot
     const int b = blockIdx.x, lane = threadIdx.x;
     if (skip && skip[b]) return;
     float2* cs = csall + (size_t)b * cap;
@@ -410,7 +409,7 @@ __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict_
         const float ee = rev ? (i < r - 1 ? eall[(size_t)b * r + r - 2 - i] : 0.f) : eall[(size_t)b * r + i];
         de[i] = make_float2(dall[(size_t)b * r + src], ee);
     }
-    for (int i = lane; i < RA_NS; i += 32) endlv[i] = 0;
+    for (int i = lane; i < nslots; i += 32) endlv[i] = 0;
     if (lane == 0) de[-1] = make_float2(0.f, 0.f);
     __syncwarp();
     const unsigned de_sa = (unsigned)__cvta_generic_to_shared(de);
@@ -491,7 +490,7 @@ __global__ void __launch_bounds__(32) tql_kernel(int r, const float* __restrict_
                     }
                     const int applied = top - i;
                     if (applied > 0) {
-                        const int slot = ns % RA_NS;
+                        const int slot = ns % nslots;
                         key = max(max(key + 2, top + 1), endlv[slot] + top);
                         const int base = key - top;
                         endlv[slot] = base + applied;
@@ -551,7 +550,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //         slot's next sweep and its first block arrive the same way in private cells. Nothing in the loop waits on a
 //         global load. Then W[i][:] = lambda_i conj(Xt[i][:]). -------------------------------------------------------
 // Each lane owns two adjacent columns (one float4): a slot's row is 128 bytes = all 32 banks, conflict-free.
-__global__ void __launch_bounds__(RA_THREADS, 3) rotapply_kernel(const float2* __restrict__ Xall, int r,
+template <int RA_NS>
+__global__ void __launch_bounds__(RA_C * RA_NS, RA_NS == 64 ? 3 : 2) rotapply_kernel(const float2* __restrict__ Xall, int r,
                                                                  const float2* __restrict__ csall,
                                                                  const SweepRec* __restrict__ swall,
                                                                  const int32_t* __restrict__ metaall,
@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(RA_THREADS, 3) rotapply_kernel(const float2* _
                                                                  int32_t* __restrict__ sweeps,
                                                                  const int32_t* __restrict__ skip) {
     extern __shared__ float4 ra_sm[];
+    constexpr int RA_THREADS = RA_C * RA_NS;
     if (skip && skip[blockIdx.y]) return;
     constexpr int C = RA_C;        // lanes per slot
     constexpr int CW = 2 * RA_C;   // columns per slab
@@ -985,13 +986,15 @@ int launch_formq(vk_context* h, cudaStream_t st, const float2* W, int B, int r, 
     return VK_OK;
 }
 
+template <int NS>
 int launch_rotapply(vk_context* h, cudaStream_t st, const float2* X, int B, int r, const EigScratch& L,
                     unsigned char* sc, float2* W, int ld, size_t wstride, int32_t* done, int32_t* sweeps,
                     const int32_t* skip) {
-    const size_t smem = (size_t)RA_THREADS * 24 + (size_t)RA_NS * 16 * 8 + (size_t)r * RA_C * sizeof(float4);
-    VK_CUDA(h, cudaFuncSetAttribute(rotapply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int THREADS = RA_C * NS;
+    const size_t smem = (size_t)THREADS * 24 + (size_t)NS * 16 * 8 + (size_t)r * RA_C * sizeof(float4);
+    VK_CUDA(h, cudaFuncSetAttribute(rotapply_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((r + 2 * RA_C - 1) / (2 * RA_C), B);
-    rotapply_kernel<<<grid, RA_THREADS, smem, st>>>(X, r, reinterpret_cast<const float2*>(sc + L.cs),
+    rotapply_kernel<NS><<<grid, THREADS, smem, st>>>(X, r, reinterpret_cast<const float2*>(sc + L.cs),
                                                     reinterpret_cast<const SweepRec*>(sc + L.sw),
                                                     reinterpret_cast<const int32_t*>(sc + L.meta),
                                                     reinterpret_cast<const float*>(sc + L.lam), W, ld, wstride, L.cap,
@@ -1056,6 +1059,9 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     if (rc) return rc;
     if (dbg) cudaEventRecord(ev[1], st);
     const int32_t* skip = nullptr;
+    // sweeps in flight in the rotation application (and in the level assignment of the QL kernel): measured 1.85 vs 2.31 ms
+    // at r = 256 with 64 vs 128 slots, 40.9 vs 35.8 ms per 296 matrices at r = 512
+    const int nslots = r <= 256 ? 64 : 128;
     if (h->topk != 1 && fixed_rank > 0 && fixed_rank <= topk_qr_limit(r)) {
         const int k = fixed_rank;
         float* lamtop = reinterpret_cast<float*>(sc + L.lamtop);
@@ -1066,11 +1072,18 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         twisted_kernel<<<B, 32, 0, st>>>(r, k, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
                                          reinterpret_cast<float*>(sc + L.dm));
         VK_LAUNCH_CHECK(h);
-        if (r <= 64) rc = launch_backtr<2, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
-        else if (r <= 128) rc = launch_backtr<4, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
-        else if (r <= 256) rc = launch_backtr<8, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
-        else if (r <= 512) rc = launch_backtr<16, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
-        else rc = launch_backtr<32, 2>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+        // vectors per warp: as few as the eight warps of the CTA allow (k <= 8: one each)
+#define VK_BACKTR(EPL)                                                                                                  \
+    (k <= 8    ? launch_backtr<EPL, 1>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev)              \
+     : k <= 16 ? launch_backtr<EPL, 2>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev)              \
+               : launch_backtr<EPL, 4>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev))
+        if (r <= 64) rc = VK_BACKTR(2);
+        else if (r <= 128) rc = VK_BACKTR(4);
+        else if (r <= 256) rc = VK_BACKTR(8);
+        else if (r <= 512) rc = VK_BACKTR(16);
+        else rc = k <= 8 ? launch_backtr<32, 1>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev)
+                         : launch_backtr<32, 2>(h, st, W, B, r, ld, wstride, k, tau, ph, L, sc, done_dev, sweeps_dev);
+#undef VK_BACKTR
         if (rc) return rc;
         skip = flag;  // the full path below takes what is left (flag 0)
     }
@@ -1078,12 +1091,12 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     // the scalar QL iteration is latency bound (one lane per matrix): it runs alone - sharing the SMs with another
     // kernel slows its dependent chain by more than the overlap wins (measured: 10.3 ms serial, 18.6 ms overlapped)
     {
-        const size_t smem = (size_t)2 * (r + 2) * 4 + (size_t)RA_NS * 4;
+        const size_t smem = (size_t)2 * (r + 2) * 4 + (size_t)RA_NS_MAX * 4;
         VK_CUDA(h, cudaFuncSetAttribute(tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tql_kernel<<<B, 32, smem, st>>>(r, d, e, reinterpret_cast<float*>(sc + L.lam),
                                         reinterpret_cast<float2*>(sc + L.cs), reinterpret_cast<SweepRec*>(sc + L.sw),
                                         reinterpret_cast<int32_t*>(sc + L.meta), L.cap, L.scap, L.lcap, skip,
-                                        h->ql_maxit > 0 ? h->ql_maxit : QL_MAXIT);
+                                        h->ql_maxit > 0 ? h->ql_maxit : QL_MAXIT, nslots);
         VK_LAUNCH_CHECK(h);
     }
     if (dbg) cudaEventRecord(ev[3], st);
@@ -1094,7 +1107,8 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     else rc = launch_formq<32, 1>(h, st, W, B, r, ld, wstride, tau, ph, X, skip);
     if (rc) return rc;
     if (dbg) cudaEventRecord(ev[4], st);
-    rc = launch_rotapply(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip);
+    rc = nslots == 64 ? launch_rotapply<64>(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip)
+                      : launch_rotapply<128>(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip);
     if (dbg) {
         cudaEventRecord(ev[5], st);
         cudaEventSynchronize(ev[5]);
