@@ -22,27 +22,12 @@ constexpr int TD_WARPS = TD_THREADS / 32;
 constexpr int FQ_THREADS = 256;
 constexpr int FQ_WARPS = FQ_THREADS / 32;
 constexpr int FQ_TJ = 8;  // reflectors staged per shared-memory tile
-constexpr int RA_C = 8;     // columns of Xt per slab = lanes per application slot
+constexpr int RA_C = 8;     // lanes per application slot (two columns of the 16-column slab each)
 constexpr int RA_NS_MAX = 128;  // application slots per CTA = sweeps in flight: 64 (r <= 256) or 128
 constexpr int QL_MAXIT = 60;
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// block-wide sum of a float2 (TD_THREADS threads), result to every thread; two barriers, the first of which also
-// publishes whatever the callers wrote to shared memory before the call
-__device__ __forceinline__ float2 block_sum2(float2 v, float2* scratch) {
-    v.x = warp_sum(v.x);
-    v.y = warp_sum(v.y);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[w] = v;
-    __syncthreads();
-    float2 t = lane < TD_WARPS ? scratch[lane] : make_float2(0.f, 0.f);
-    t.x = warp_sum(t.x);
-    t.y = warp_sum(t.y);
-    return t;
 }
 
 // ---- 1. tridiagonalisation: one CTA per matrix, matrix in global memory (L2). The two-sided rank-2 update of step
