@@ -265,6 +265,278 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
     }
 }
 
+// ---- 1b. the same reduction touching only the lower triangle (the default): a pass reads and writes the elements
+//          (i, k), j < k <= i, once, which halves the traffic and two thirds of the arithmetic. Element x = A(i, k)
+//          contributes x v_k to (A v)_i (row part, reduced over the lanes of the warp that owns row i) and, for k < i,
+//          conj(x) v_i to (A v)_k (column part, accumulated per lane - a lane owns the columns k = 32 e + lane - and
+//          summed over the warps through shared memory). v^H A v = 2 Re sum_i conj(v_i) rowpart_i - sum_i |v_i|^2 A(i, i)
+//          needs the row parts only. The column below the next pivot and the next diagonal element are collected by the
+//          pass; the reflectors go to the (otherwise unused) upper triangle where formq / backtr expect them.
+//          Once the trailing block fits it is expanded to a full square in shared memory (resident steps). -------------
+template <int EPL, int RB>
+__global__ void __launch_bounds__(TD_THREADS, 1)
+    tridiag_sym_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
+                       float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
+    constexpr int WD = EPL * 32;
+    extern __shared__ float2 td_sm[];
+    float2* vprev = td_sm;
+    float2* vnew = td_sm + WD;
+    float2* wv = td_sm + 2 * WD;
+    float2* pv = td_sm + 3 * WD;      // row parts of A v (unscaled)
+    float2* acol = td_sm + 4 * WD;    // column j+1 below the diagonal as the pass of step j left it
+    float2* pc = td_sm + 5 * WD;      // [TD_WARPS][WD] per-warp column parts of A v
+    float2* T = pc + TD_WARPS * WD;   // [ts][ts] resident trailing block (full square), rows/cols j0 .. r-1
+    int j0 = -1, ts = 0;
+    __shared__ float s_part[TD_WARPS];
+    __shared__ float4 s_kpart[TD_WARPS];  // (Re, Im of sum conj(v_i) rowpart_i, sum |v_i|^2 A_ii, -)
+    __shared__ float2 s_alpha;
+    __shared__ float s_diag;              // A(j+1, j+1) as the pass of step j left it
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* M = Wall + (size_t)b * wstride;
+    float* d = dall + (size_t)b * r;
+    float* e = eall + (size_t)b * r;
+    float* taus = tauall + (size_t)b * r;
+    float2* ph = phall + (size_t)b * r;
+    float2 phase = make_float2(1.f, 0.f);
+    if (tid == 0) ph[0] = phase;
+    for (int k = tid; k < (5 + TD_WARPS) * WD; k += TD_THREADS) td_sm[k] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    for (int j = 0; j + 2 < r; ++j) {
+        const int e0 = (j + 1) >> 5;
+        if (j0 < 0 && r - j <= nts) {
+            j0 = j, ts = r - j;
+            for (int idx = tid; idx < ts * ts; idx += TD_THREADS) {
+                const int i = idx / ts, k = idx - i * ts;
+                float2 v;
+                if (k <= i) {
+                    v = M[(size_t)(j0 + i) * ld + j0 + k];
+                } else {
+                    v = M[(size_t)(j0 + k) * ld + j0 + i];
+                    v.y = -v.y;
+                }
+                T[idx] = v;
+            }
+            __syncthreads();
+        }
+        const bool resident = j0 >= 0;
+        // column j below the diagonal and the diagonal element, with the pending update of step j-1 applied
+        float ss = 0.f;
+        {
+            const float2 vj = vprev[j], wj = wv[j];  // zero while j == 0
+            for (int k = tid; k < WD; k += TD_THREADS) {
+                float2 a = make_float2(0.f, 0.f);
+                if (k > j && k < r) {
+                    float2 x = (j == 0) ? M[(size_t)k * ld] : acol[k];
+                    const float2 vk = vprev[k], wk = wv[k];
+                    x.x -= vk.x * wj.x + vk.y * wj.y + wk.x * vj.x + wk.y * vj.y;
+                    x.y -= vk.y * wj.x - vk.x * wj.y + wk.y * vj.x - wk.x * vj.y;
+                    a = x;
+                    ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                    if (k == j + 1) s_alpha = a;
+                } else if (k == j) {
+                    float xd = (j == 0) ? M[0].x : s_diag;
+                    xd -= 2.f * (vj.x * wj.x + vj.y * wj.y);
+                    d[j] = xd;
+                }
+                vnew[k] = a;
+            }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_part[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) tot += s_part[w];
+        float tau = 0.f;
+        {
+            float ej = 0.f;
+            float2 v0 = s_alpha;
+            if (tot > 1e-30f) {
+                const float xn = sqrtf(tot);
+                const float2 alpha = v0;
+                const float aa = sqrtf(alpha.x * alpha.x + alpha.y * alpha.y);
+                float2 p1 = make_float2(1.f, 0.f);
+                if (aa > 0.f) p1 = make_float2(alpha.x / aa, alpha.y / aa);
+                v0 = make_float2(alpha.x + p1.x * xn, alpha.y + p1.y * xn);
+                tau = 1.f / (xn * (xn + aa));
+                ej = xn;
+                phase = cmulf(phase, make_float2(-p1.x, -p1.y));  // sub-diagonal element is -p1 * xn
+            }
+            if (tid == 0) {
+                vnew[j + 1] = v0;
+                taus[j] = tau;
+                e[j] = ej;
+                ph[j + 1] = phase;
+            }
+        }
+        __syncthreads();
+        // the reflector goes to row j right of the diagonal (upper triangle: not part of the working storage)
+        {
+            float2* row = M + (size_t)j * ld;
+            for (int k = j + 1 + tid; k < r; k += TD_THREADS) row[k] = vnew[k];
+        }
+        float2 kacc = make_float2(0.f, 0.f);  // sum conj(v_i) rowpart_i over this warp's rows (same on all lanes)
+        float kd = 0.f;                       // sum |v_i|^2 A(i, i) (per lane, reduced below)
+        if (resident) {
+            for (int i = j + 1 + warp; i < r; i += TD_WARPS) {
+                float2* row = T + (size_t)(i - j0) * ts - j0;
+                const float2 vi = vprev[i], wi = wv[i];
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+                for (int k = j + 1 + lane; k < r; k += 32) {
+                    float2 t = row[k];
+                    const float2 wk = wv[k], vk = vprev[k];
+                    t.x -= vi.x * wk.x + vi.y * wk.y + wi.x * vk.x + wi.y * vk.y;
+                    t.y -= vi.y * wk.x - vi.x * wk.y + wi.y * vk.x - wi.x * vk.y;
+                    row[k] = t;
+                    if (i == j + 1) {
+                        if (k == j + 1) s_diag = t.x;
+                        else acol[k] = make_float2(t.x, -t.y);  // column j+1 = conj(row j+1)
+                    }
+                    cfma(acc, t, vnew[k]);
+                }
+                acc.x = warp_sum(acc.x);
+                acc.y = warp_sum(acc.y);
+                const float2 v = vnew[i];
+                kacc.x += v.x * acc.x + v.y * acc.y;
+                kacc.y += v.x * acc.y - v.y * acc.x;
+                if (lane == 0) pv[i] = acc;
+            }
+        } else {
+            float2 pcr[EPL];
+#pragma unroll
+            for (int ee = 0; ee < EPL; ++ee) pcr[ee] = make_float2(0.f, 0.f);
+            for (int ib = j + 1 + warp; ib < r; ib += TD_WARPS * RB) {
+                float2 x[RB][EPL];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int i = ib + q * TD_WARPS;
+                    const float2* row = M + (size_t)i * ld;
+#pragma unroll
+                    for (int ee = 0; ee < EPL; ++ee) {
+                        const int k = ee * 32 + lane;
+                        x[q][ee] = (ee >= e0 && k > j && k <= i && i < r) ? row[k] : make_float2(0.f, 0.f);
+                    }
+                }
+                float2 vi[RB], wi[RB], vni[RB], acc[RB];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int i = ib + q * TD_WARPS;
+                    const bool ok = i < r;
+                    vi[q] = ok ? vprev[i] : make_float2(0.f, 0.f);
+                    wi[q] = ok ? wv[i] : make_float2(0.f, 0.f);
+                    vni[q] = ok ? vnew[i] : make_float2(0.f, 0.f);
+                    acc[q] = make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int ee = 0; ee < EPL; ++ee) {
+                    const int k = ee * 32 + lane;
+                    if (ee >= e0 && k > j && k < r) {
+                        const float2 wk = wv[k], vk = vprev[k], vn = vnew[k];
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) {
+                            const int i = ib + q * TD_WARPS;
+                            if (k <= i && i < r) {
+                                float2 t = x[q][ee];
+                                t.x -= vi[q].x * wk.x + vi[q].y * wk.y + wi[q].x * vk.x + wi[q].y * vk.y;
+                                t.y -= vi[q].y * wk.x - vi[q].x * wk.y + wi[q].y * vk.x - wi[q].x * vk.y;
+                                x[q][ee] = t;
+                                cfma(acc[q], t, vn);
+                                if (k < i) {
+                                    // column part: conj(t) * v_i
+                                    pcr[ee].x = fmaf(t.x, vni[q].x, fmaf(t.y, vni[q].y, pcr[ee].x));
+                                    pcr[ee].y = fmaf(t.x, vni[q].y, fmaf(-t.y, vni[q].x, pcr[ee].y));
+                                    if (k == j + 1) acol[i] = t;
+                                } else {
+                                    kd = fmaf(vni[q].x * vni[q].x + vni[q].y * vni[q].y, t.x, kd);
+                                    if (i == j + 1) s_diag = t.x;
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int i = ib + q * TD_WARPS;
+                    if (i < r) {
+                        if (j > 0) {
+                            float2* row = M + (size_t)i * ld;
+#pragma unroll
+                            for (int ee = 0; ee < EPL; ++ee) {
+                                const int k = ee * 32 + lane;
+                                if (ee >= e0 && k > j && k <= i) row[k] = x[q][ee];
+                            }
+                        }
+                        const float ax = warp_sum(acc[q].x), ay = warp_sum(acc[q].y);
+                        kacc.x += vni[q].x * ax + vni[q].y * ay;
+                        kacc.y += vni[q].x * ay - vni[q].y * ax;
+                        if (lane == 0) pv[i] = make_float2(ax, ay);
+                    }
+                }
+            }
+#pragma unroll
+            for (int ee = 0; ee < EPL; ++ee) pc[warp * WD + ee * 32 + lane] = pcr[ee];
+            kd = warp_sum(kd);
+        }
+        if (lane == 0) s_kpart[warp] = make_float4(kacc.x, kacc.y, kd, 0.f);
+        __syncthreads();
+        // v^H A v (real), K = tau^2/2 * v^H A v, p = tau * (row part + column parts), w = p - K v
+        float kre = 0.f, kdd = 0.f;
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) kre += s_kpart[w].x, kdd += s_kpart[w].z;
+        const float vav = resident ? kre : 2.f * kre - kdd;
+        const float K = 0.5f * tau * tau * vav;
+        for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
+            float2 p = pv[k];
+            if (!resident) {
+#pragma unroll
+                for (int w = 0; w < TD_WARPS; ++w) {
+                    const float2 c = pc[w * WD + k];
+                    p.x += c.x, p.y += c.y;
+                }
+            }
+            const float2 v = vnew[k];
+            wv[k] = make_float2(tau * p.x - K * v.x, tau * p.y - K * v.y);
+        }
+        float2* t = vprev;
+        vprev = vnew;
+        vnew = t;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (r == 1) {
+            d[0] = M[0].x;
+        } else {
+            const int j = r - 2;
+            // (j, j), (j+1, j) and (j+1, j+1) with the pending update of step j-1 = r-3 applied
+            float x00, x11;
+            float2 x10;
+            if (r >= 3) {
+                x00 = s_diag;
+                x10 = acol[j + 1];
+                x11 = j0 >= 0 ? T[(size_t)(j + 1 - j0) * ts + j + 1 - j0].x : M[(size_t)(j + 1) * ld + j + 1].x;
+                const float2 v0 = vprev[j], v1 = vprev[j + 1], w0 = wv[j], w1 = wv[j + 1];
+                x00 -= 2.f * (v0.x * w0.x + v0.y * w0.y);
+                x11 -= 2.f * (v1.x * w1.x + v1.y * w1.y);
+                x10.x -= v1.x * w0.x + v1.y * w0.y + w1.x * v0.x + w1.y * v0.y;
+                x10.y -= v1.y * w0.x - v1.x * w0.y + w1.y * v0.x - w1.x * v0.y;
+            } else {
+                x00 = M[0].x, x10 = M[(size_t)ld], x11 = M[(size_t)ld + 1].x;
+            }
+            d[j] = x00;
+            d[j + 1] = x11;
+            const float ea = sqrtf(x10.x * x10.x + x10.y * x10.y);  // sub-diagonal element
+            e[j] = ea;
+            if (ea > 0.f) phase = cmulf(phase, make_float2(x10.x / ea, x10.y / ea));
+            ph[j + 1] = phase;
+            taus[j] = 0.f;
+        }
+        e[r - 1] = 0.f;
+        taus[r - 1] = 0.f;
+    }
+}
+
 // ---- 2. Xt0 = (Q D)^T: row i = H_0 ... H_{r-3} e_i, kept in the registers of one warp for all reflectors -------------
 template <int EPL, int RPW>
 __global__ void __launch_bounds__(FQ_THREADS, (EPL <= 16) ? 2 : 1)
@@ -960,6 +1232,20 @@ int launch_tridiag(vk_context* h, cudaStream_t st, float2* W, int B, int r, int 
     return VK_OK;
 }
 
+template <int EPL, int RB>
+int launch_tridiag_sym(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
+                       float* tau, float2* ph) {
+    const size_t vec = (size_t)(5 + TD_WARPS) * EPL * 32 * sizeof(float2);
+    int nts = (int)sqrt((double)(VK_SMEM_BUDGET - vec) / sizeof(float2));
+    if (nts > r) nts = r;
+    if (r > 384) nts = 0;  // see launch_tridiag
+    const size_t smem = vec + (size_t)nts * nts * sizeof(float2);
+    VK_CUDA(h, cudaFuncSetAttribute(tridiag_sym_kernel<EPL, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tridiag_sym_kernel<EPL, RB><<<B, TD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 template <int EPL, int RPW>
 int launch_formq(vk_context* h, cudaStream_t st, const float2* W, int B, int r, int ld, size_t wstride, const float* tau,
                  const float2* ph, float2* X, const int32_t* skip) {
@@ -1036,7 +1322,10 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     const bool dbg = h->stage_timing >= 1;  // per-kernel event times (vk_last_eig_ms; also on stderr at level 2)
     cudaEvent_t* ev = h->eig_ev;
     if (dbg) cudaEventRecord(ev[0], st);
-    if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    // lower-triangle variant where it wins: 256 < r <= 512 (32.0 vs 35.3 ms per 296 matrices at r = 512; at r <= 256 the
+    // full-storage kernel is faster, 1.98 vs 2.07 ms for 112 matrices of r = 256, above 512 it would spill)
+    if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 128) rc = launch_tridiag<4, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 256) rc = launch_tridiag<8, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 512) rc = launch_tridiag<16, 2>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
