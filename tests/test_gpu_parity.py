@@ -485,3 +485,47 @@ def test_direct_solver_hands_unconverged_passes_to_jacobi(eng, torch):
     assert float(got[4][:, 3].min()) == 1 and float(got[4][:, 2].max()) <= 30   # converged, in Jacobi sweeps
     assert torch.equal(got[3], base[3])
     assert float(((got[1] - base[1]).abs() / base[1].clamp_min(1e-20)).max()) < 1e-4
+
+
+def test_ill_conditioned_matrices_are_redone_without_a_gram_product(eng, torch):
+    """A float32 Gram matrix resolves eigenvalues only down to ~1e-7 of the largest one: singular values a few 1e-3 below
+    sigma_1 would come out wrong (and their vectors mixed). Matrices whose RETAINED values reach that far are detected and
+    done again by one-sided Jacobi on the matrix itself; the result has to meet the same tolerances as everywhere."""
+    rng = np.random.default_rng(42)
+    m, n = 150, 268
+    Q1, _ = np.linalg.qr(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    sv = np.sort(np.concatenate([100.0 * (1 + rng.random(5)), 0.05 * (0.5 + rng.random(m - 5))]))[::-1]
+    A = np.stack([((Q1 * sv[None, :]) @ Q2[:m]).astype(np.complex64),
+                  (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))).astype(np.complex64)])
+    Ad = torch.from_numpy(A).cuda()
+    for kw in (dict(compressionrank=24), dict(), dict(decorrelation=0.9999999)):
+        U, S, Vt, ranks, stats = eng.compress(Ad, **kw)
+        torch.cuda.synchronize()
+        Uh, Sh, Vh, rk, st = (x.cpu().numpy() for x in (U, S, Vt, ranks, stats))
+        assert np.all(st[:, 3] == 1)
+        for b in range(2):
+            k = int(rk[b])
+            parity.check_factors(A[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"ill-conditioned {kw} b={b}", **kw)
+    # the well-conditioned matrix of the batch and a truncation that stops above the gap do not take the detour
+    eng.set_option("illcond_thr", 0.0)
+    try:
+        U0, S0, Vt0, r0, _ = eng.compress(Ad, compressionrank=5)
+    finally:
+        eng.set_option("illcond_thr", 0.005)
+    U1, S1, Vt1, r1, _ = eng.compress(Ad, compressionrank=5)
+    assert torch.equal(S0, S1) and torch.equal(r0, r1)
+
+
+def test_odd_row_count_with_large_rank(eng, torch):
+    """m odd, kmax > 16 and n % 16 == 0: the tcgen05 V-formation cannot take an odd m (16-byte tensor-map strides), the
+    SIMT GEMM has to (found by tools/stress_parity.py: the call used to fail with a tensor-map error)."""
+    for (m, n, k) in [(147, 528, 18), (137, 208, 40)]:
+        A = _device_cube(eng, torch, 1, 2, m, n)
+        U, S, Vt, ranks, stats = eng.compress(A, compressionrank=k)
+        out = eng.reconstruct(U, S, Vt, ranks)
+        torch.cuda.synchronize()
+        Ah, Uh, Sh, Vh, oh = (x.cpu().numpy() for x in (A, U, S, Vt, out))
+        for b in range(2):
+            parity.check_factors(Ah[b], Uh[b], Sh[b], Vh[b], k, compressionrank=k, label=f"{m}x{n} k={k}")
+            parity.check_reconstruction(Uh[b], Sh[b], Vh[b], oh[b], label=f"{m}x{n} k={k}")

@@ -1,0 +1,71 @@
+"""Dev / release check (GPU): randomized parity sweep of the whole compress path against the oracle — random shapes on
+both sides of the small-path / Gram-path / eigensolver boundaries, all three rank rules, matrices of different character
+(signal dominated, pure noise, exactly low rank, badly scaled). Usage: stress_parity.py [ncases] [seed]"""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from tests import parity  # noqa: E402
+from visco_b200.engine import get_engine  # noqa: E402
+
+
+def make(rng, kind, m, n):
+    g = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    r = min(m, n)
+    if kind == "noise":
+        a = g(m, n)
+    elif kind == "signal":
+        k = int(rng.integers(1, max(2, r // 4)))
+        a = g(m, k) @ (np.diag(10.0 ** rng.uniform(0, 2, k)) @ g(k, n)) / np.sqrt(k) + 0.1 * g(m, n)
+    elif kind == "lowrank":
+        k = int(rng.integers(1, max(2, min(6, r))))
+        a = g(m, k) @ g(k, n)
+    else:  # "scaled": huge dynamic range between matrices of a batch
+        a = g(m, n) * 10.0 ** rng.uniform(-4, 4)
+    return a.astype(np.complex64)
+
+
+def main():
+    ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    eig_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    rng = np.random.default_rng(seed)
+    eng = get_engine(0)
+    eng.set_option("eig_impl", eig_impl)
+    t0 = time.time()
+    fails = 0
+    for case in range(ncases):
+        big = rng.random() < 0.2
+        m = int(rng.integers(2, 700 if big else 200))
+        n = int(rng.integers(2, 700 if big else 300))
+        r = min(m, n)
+        mode = rng.choice(["fixed", "energy", "full"], p=[0.5, 0.35, 0.15])
+        kw = {}
+        if mode == "fixed":
+            kw["compressionrank"] = int(rng.integers(1, min(r, 40) + 1))
+        elif mode == "energy":
+            kw["decorrelation"] = float(rng.choice([0.5, 0.9, 0.98, 0.999]))
+        kinds = ["noise", "signal", "lowrank", "scaled"]
+        A = np.stack([make(rng, kinds[(case + b) % 4], m, n) for b in range(4)])
+        try:
+            Ad = torch.from_numpy(A).cuda()
+            U, S, Vt, ranks, stats = eng.compress(Ad, **kw)
+            out = eng.reconstruct(U, S, Vt, ranks)
+            torch.cuda.synchronize()
+            Uh, Sh, Vh, rk, st, oh = (x.cpu().numpy() for x in (U, S, Vt, ranks, stats, out))
+            assert np.all(st[:, 3] == 1), "not converged"
+            for b in range(4):
+                k = int(rk[b])
+                parity.check_factors(A[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"case {case} {m}x{n} {kw} b={b}", **kw)
+                parity.check_reconstruction(Uh[b, :, :k], Sh[b, :k], Vh[b, :k], oh[b], label=f"case {case} recon")
+        except Exception as ex:  # noqa: BLE001
+            fails += 1
+            print(f"FAIL case {case}: {m}x{n} {kw}: {type(ex).__name__}: {str(ex)[:300]}", flush=True)
+    print(f"{ncases - fails}/{ncases} cases passed in {time.time() - t0:.1f} s (seed {seed})")
+    return 1 if fails else 0
+
+
+sys.exit(main())

@@ -1,6 +1,8 @@
 // C ABI of libvisco_b200.so (see include/visco_b200.h). Orchestrates the stages; no arithmetic here.
+#include <algorithm>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,14 +30,14 @@ bool use_qr(const vk_context* h, int m, int n, int fixed_rank = 0) {
     return true;
 }
 
-WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false) {
+WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false, bool direct = false) {
     if (gchunk < chunk) gchunk = chunk;
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
     WsLayout w;
     size_t off = 0;
-    const size_t wbytes = small_path(m, n) ? (size_t)gchunk * r * (L + r) * sizeof(float2)
-                                           : (size_t)gchunk * r * r * sizeof(float2);
+    const size_t wbytes = (small_path(m, n) || direct) ? (size_t)gchunk * r * (L + r) * sizeof(float2)
+                                                       : (size_t)gchunk * r * r * sizeof(float2);
     w.W = off, off += align_up(wbytes);
     w.perm = off, off += align_up((size_t)chunk * r * 4);
     w.inv = off, off += align_up((size_t)chunk * r * 4);
@@ -48,7 +50,8 @@ WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = 
     w.norm2 = off, off += align_up((size_t)chunk * kmax * 4);
     // K-major copy of conj(U_k)^T for the tcgen05 V-formation (wide Gram path, k > 8)
     w.xbuf = off;
-    if (!small_path(m, n) && m <= n && vk_cgemm_tc_supported(m, n, kmax)) off += align_up((size_t)chunk * kmax * m * 8);
+    if (!small_path(m, n) && !direct && m <= n && vk_cgemm_tc_supported(m, n, kmax))
+        off += align_up((size_t)chunk * kmax * m * 8);
     w.eig = off;
     if (qr) off += align_up(vk_eigqr_scratch_bytes(chunk, r));
     w.total = off;
@@ -137,11 +140,12 @@ int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, f
 
 int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
                    float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws, const WsLayout& L,
-                   int sub0 = 0, bool gram_done = false, bool force_jacobi = false) {
+                   int sub0 = 0, bool gram_done = false, bool force_jacobi = false, bool direct = false) {
     // sub0: index of this chunk's first matrix inside the Gram super-chunk (W and gscale are laid out per super-chunk)
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
-    float2* W = reinterpret_cast<float2*>(ws + L.W) + (small_path(m, n) ? 0 : (size_t)sub0 * r * r);
+    const bool no_gram = small_path(m, n) || direct;  // one-sided Jacobi on the matrix itself
+    float2* W = reinterpret_cast<float2*>(ws + L.W) + (no_gram ? 0 : (size_t)sub0 * r * r);
     int32_t* perm = reinterpret_cast<int32_t*>(ws + L.perm);
     float* inv = reinterpret_cast<float*>(ws + L.inv);
     float* gscale = reinterpret_cast<float*>(ws + L.gscale) + sub0;
@@ -154,7 +158,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
     int rc;
     StageTimer tm(h);
     if (!gram_done) VK_CUDA(h, cudaMemsetAsync(nonfinite, 0, 4, h->stream));
-    if (small_path(m, n)) {
+    if (no_gram) {
         const int Llong = m < n ? n : m;
         const JacobiPlan p = vk_jacobi_plan(h, r, Llong, Llong + r);
         tm.mark(0);
@@ -199,7 +203,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         tm.collect(3, 3, 4);
     }
     // poll: non-finite input, and whether the direct eigensolver gave a matrix up (QL iteration limit, rotation store)
-    const bool qr_used = !small_path(m, n) && use_qr(h, m, n, fixed_rank) && !force_jacobi;
+    const bool qr_used = !no_gram && use_qr(h, m, n, fixed_rank) && !force_jacobi;
     if (h->check_finite || qr_used) {
         h->h_poll[2] = 0;
         if (qr_used) {
@@ -215,6 +219,70 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
             return compress_chunk(h, A, B, m, n, fixed_rank, decorrelation, kmax, U, S, Vt, ranks, stats, ws, L, sub0, false,
                                   true);
         }
+    }
+    return VK_OK;
+}
+
+// Matrices whose retained singular values reach below illcond_thr * sigma_1 cannot be resolved through a float32 Gram
+// matrix (lambda is only known to ~1e-7 lambda_max). They are rare in this application (the truncation normally stops
+// far above that), so they are simply done again by the small-matrix method - one-sided Jacobi on the matrix itself,
+// vectors streamed from global memory - in sub-batches gathered into a second workspace, and their results replace the
+// first ones. One 4-byte poll per call when nothing is flagged.
+int redo_ill_conditioned(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation,
+                         int kmax, float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws,
+                         const WsLayout& L) {
+    int rc;
+    // flags live behind the per-chunk bookkeeping of the main workspace: reuse perm (chunk * r ints >= B? not always)
+    const size_t fbytes = align_up((size_t)B * 4) + 256;
+    if ((rc = ensure(h, &h->ws2, &h->ws2_bytes, fbytes))) return rc;
+    int32_t* flags = static_cast<int32_t*>(h->ws2);
+    int32_t* count = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(h->ws2) + align_up((size_t)B * 4));
+    (void)ws;
+    (void)L;
+    if ((rc = vk_launch_flag_illcond(h, S, ranks, B, kmax, h->illcond_thr, flags, count))) return rc;
+    VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 3, count, 4, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const int nflag = h->h_poll[3];
+    if (nflag <= 0) return VK_OK;
+    std::vector<int32_t> hf((size_t)B);
+    VK_CUDA(h, cudaMemcpy(hf.data(), flags, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    std::vector<int> idx;
+    for (int b = 0; b < B; ++b)
+        if (hf[b]) idx.push_back(b);
+    const size_t bA = (size_t)m * n * 8, bU = (size_t)m * kmax * 8, bS = (size_t)kmax * 4, bV = (size_t)kmax * n * 8;
+    const size_t per = align_up(bA) + align_up(bU) + align_up(bS) + align_up(bV) + 512 +
+                       ws_layout(1, m, n, kmax, 1, false, true).total;
+    int cap = (int)(((size_t)2 << 30) / per);
+    if (cap < 1) cap = 1;
+    if (cap > (int)idx.size()) cap = (int)idx.size();
+    const WsLayout Ld = ws_layout(cap, m, n, kmax, cap, false, true);
+    const size_t oA = 0, oU = oA + align_up(bA * cap), oS = oU + align_up(bU * cap), oV = oS + align_up(bS * cap),
+                 oR = oV + align_up(bV * cap), oT = oR + align_up((size_t)cap * 4), oW = oT + align_up((size_t)cap * 16);
+    if ((rc = ensure(h, &h->ws2, &h->ws2_bytes, oW + Ld.total))) return rc;
+    unsigned char* p = static_cast<unsigned char*>(h->ws2);
+    float2* A2 = reinterpret_cast<float2*>(p + oA);
+    float2* U2 = reinterpret_cast<float2*>(p + oU);
+    float* S2 = reinterpret_cast<float*>(p + oS);
+    float2* V2 = reinterpret_cast<float2*>(p + oV);
+    int32_t* R2 = reinterpret_cast<int32_t*>(p + oR);
+    float* T2 = reinterpret_cast<float*>(p + oT);
+    cudaStream_t st = h->stream;
+    for (size_t s0 = 0; s0 < idx.size(); s0 += cap) {
+        const int nb = (int)std::min((size_t)cap, idx.size() - s0);
+        for (int i = 0; i < nb; ++i)
+            VK_CUDA(h, cudaMemcpyAsync(A2 + (size_t)i * m * n, A + (size_t)idx[s0 + i] * m * n, bA, cudaMemcpyDeviceToDevice, st));
+        if ((rc = compress_chunk(h, A2, nb, m, n, fixed_rank, decorrelation, kmax, U2, S2, V2, R2, T2, p + oW, Ld, 0, false,
+                                 false, true)))
+            return rc;
+        for (int i = 0; i < nb; ++i) {
+            const size_t b = (size_t)idx[s0 + i];
+            VK_CUDA(h, cudaMemcpyAsync(U + b * m * kmax, U2 + (size_t)i * m * kmax, bU, cudaMemcpyDeviceToDevice, st));
+            VK_CUDA(h, cudaMemcpyAsync(S + b * kmax, S2 + (size_t)i * kmax, bS, cudaMemcpyDeviceToDevice, st));
+            VK_CUDA(h, cudaMemcpyAsync(Vt + b * kmax * n, V2 + (size_t)i * kmax * n, bV, cudaMemcpyDeviceToDevice, st));
+            VK_CUDA(h, cudaMemcpyAsync(ranks + b, R2 + i, 4, cudaMemcpyDeviceToDevice, st));
+            VK_CUDA(h, cudaMemcpyAsync(stats + b * 4, T2 + (size_t)i * 4, 16, cudaMemcpyDeviceToDevice, st));
+        }
+        h->illcond_redone += nb;
     }
     return VK_OK;
 }
@@ -270,6 +338,7 @@ int vk_destroy(vk_handle h) {
     cudaStreamSynchronize(h->stream);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
+    if (h->ws2) cudaFree(h->ws2);
     if (h->h_poll) cudaFreeHost(h->h_poll);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -335,6 +404,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "ql_maxit")
         h->ql_maxit = (int)v;
+    else if (k == "illcond_thr")
+        h->illcond_thr = (float)v;
     else if (k == "chunk")
         h->chunk = (int)v;
     else
@@ -415,6 +486,10 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
                                 stats + (size_t)b0 * 4, wsp, L, s0, gram_path);
             if (rc) return rc;
         }
+    }
+    if (gram_path && h->illcond_thr > 0.f) {
+        rc = redo_ill_conditioned(h, Ap, B, m, n, fixed_rank, decorrelation, kmax, Up, S, Vp, ranks, stats, wsp, L);
+        if (rc) return rc;
     }
     if (h->stage_timing) {
         cudaEventRecord(e1, h->stream);

@@ -45,6 +45,13 @@ struct vk_context {
     int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
     int ql_maxit = 60;       // QL iterations allowed per eigenvalue (tests lower it to exercise the Jacobi fallback)
     int64_t eig_fallbacks = 0;  // internal passes the direct solver handed back to the Jacobi solver
+    // retained sigma_k / sigma_1 below this: redo the matrix without a Gram product (0 = never). Measured error of
+    // sigma_k through the float32 Gram path (tools/illcond_probe.py): 5e-6 at a ratio of 0.008, 2e-5 at 0.005, 9e-5 at
+    // 0.004, 4e-4 at 0.0024, 2e-2 at 0.0007
+    float illcond_thr = 0.005f;
+    int64_t illcond_redone = 0; // matrices redone that way since the handle was created
+    void* ws2 = nullptr;        // grow-only device workspace of that path
+    size_t ws2_bytes = 0;
     float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     float eig_ms[5] = {0, 0, 0, 0, 0};  // direct eigensolver: tridiag, leading pairs, QL, reflector accumulation, rotations
     cudaEvent_t eig_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -134,6 +141,8 @@ int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int
                      const int32_t* done_dev);
 int vk_launch_pack_info(vk_context* h, const int32_t* sweeps, const int32_t* done, int B, int32_t* info);
 int vk_launch_count_not_done(vk_context* h, const int32_t* done, int B, int32_t* out);
+int vk_launch_flag_illcond(vk_context* h, const float* S, const int32_t* ranks, int B, int kmax, float thr, int32_t* flags,
+                           int32_t* count);
 int vk_launch_find_n(vk_context* h, const float* S, int B, int r, double decorrelation, int32_t* ranks);
 
 // factor formation

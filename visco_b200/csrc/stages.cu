@@ -742,6 +742,30 @@ __global__ void count_not_done_kernel(const int32_t* __restrict__ done, int B, i
     }
 }
 
+// flags[b] = 1 when the smallest retained singular value of matrix b is below thr * the largest: the Gram matrix (float32)
+// resolves lambda only down to ~1e-7 lambda_max, i.e. sigma down to a few 1e-2 sigma_max at the 1e-4 relative level
+__global__ void flag_illcond_kernel(const float* __restrict__ S, const int32_t* __restrict__ ranks, int B, int kmax,
+                                    float thr, int32_t* __restrict__ flags, int32_t* __restrict__ count) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int k = ranks[b];
+    int f = 0;
+    if (k > 1) {
+        const float s0 = S[(size_t)b * kmax], sk = S[(size_t)b * kmax + k - 1];
+        f = (s0 > 0.f && sk < thr * s0) ? 1 : 0;
+    }
+    flags[b] = f;
+    if (f) atomicAdd(count, 1);
+}
+
+int vk_launch_flag_illcond(vk_context* h, const float* S, const int32_t* ranks, int B, int kmax, float thr, int32_t* flags,
+                           int32_t* count) {
+    VK_CUDA(h, cudaMemsetAsync(count, 0, sizeof(int32_t), h->stream));
+    flag_illcond_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(S, ranks, B, kmax, thr, flags, count);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 int vk_launch_count_not_done(vk_context* h, const int32_t* done, int B, int32_t* out) {
     count_not_done_kernel<<<1, 256, 0, h->stream>>>(done, B, out);
     VK_LAUNCH_CHECK(h);
@@ -810,7 +834,8 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
         if ((rc = launch_cols(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 0, 1, U, B))) return rc;
         FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
         const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16 == 0);
-        if (xbuf && h->gemm_impl == 0 && kmax > 16 && vk_cgemm_tc_supported(m, n, kmax)) {
+        // (the K-major operand X has rows of m complex numbers: its tensor map needs 16-byte strides, i.e. an even m)
+        if (xbuf && h->gemm_impl == 0 && kmax > 16 && (m % 2) == 0 && vk_cgemm_tc_supported(m, n, kmax)) {
             // large rank: X = conj(U_k)^T / lambda materialised K-major, then the tcgen05 complex GEMM
             if ((rc = launch_rows(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 1, 1, xbuf, B))) return rc;
             rc = vk_launch_formv_tc(h, xbuf, A, ranks_dev, Vt, norm2_dev, B, m, n, kmax);
