@@ -33,8 +33,10 @@ __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
 // ---- 1. tridiagonalisation: one CTA per matrix, matrix in global memory (L2). The two-sided rank-2 update of step
 //         j-1 is fused with the matrix-vector product of step j: one read + one write of the trailing block per step.
 //         Lane l of a warp owns the absolute columns k = 32 e + l; a warp stages RB whole rows in registers before it
-//         touches them, so RB * (r - j) / 32 loads per lane are in flight (the kernel is L2-latency bound otherwise).
-//         All shared vectors are indexed by absolute column. -------------------------------------------------------
+//         touches them, so RB * (r - j) / 32 loads per lane are in flight. Four barriers per step: every thread sums the
+//         per-warp partials and repeats the scalar work, v^H p is accumulated inside the pass. Once the trailing block
+//         fits next to the vectors it moves to shared memory for good (r <= 384). All shared vectors are indexed by
+//         absolute column. Used for r <= 256 and r > 512. ---------------------------------------------------------
 template <int EPL, int RB>
 __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
     tridiag_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(TD_THREADS, (EPL * RB <= 8) ? 2 : 1)
     }
 }
 
-// ---- 1b. the same reduction touching only the lower triangle (the default): a pass reads and writes the elements
+// ---- 1b. the same reduction touching only the lower triangle (used for 256 < r <= 512): a pass reads and writes the elements
 //          (i, k), j < k <= i, once, which halves the traffic and two thirds of the arithmetic. Element x = A(i, k)
 //          contributes x v_k to (A v)_i (row part, reduced over the lanes of the warp that owns row i) and, for k < i,
 //          conj(x) v_i to (A v)_k (column part, accumulated per lane - a lane owns the columns k = 32 e + lane - and
@@ -801,12 +803,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ---- 4. apply the rotations to a slab of RA_C columns of Xt held in shared memory, level by level (one barrier per
 //         level). Slot q (RA_C lanes) follows the sweeps q, q + NS, q + 2 NS, ...: at level base + u it rotates rows
 //         (top - u, top - u + 1); the row shared by consecutive rotations stays in a register, so a rotation costs one
-//         shared-memory load and one store per column. The four slots of a warp work two rows apart: the 64-byte row
-//         halves of each 128-byte line are XOR-swizzled with bit 1 of the row so that they hit disjoint banks.
+//         shared-memory load and one store per column. Each lane owns two adjacent columns (one float4): a slot's row is
+//         128 bytes = all 32 banks, so the four slots of a warp serialise without bank conflicts (one column per lane
+//         put them two rows = 128 bytes apart on the same banks). NS = 64 slots per CTA for r <= 256, 128 above.
 //         (c, s) come from a 16-entry FIFO per slot that cp.async refills one block of eight ahead; the record of the
 //         slot's next sweep and its first block arrive the same way in private cells. Nothing in the loop waits on a
 //         global load. Then W[i][:] = lambda_i conj(Xt[i][:]). -------------------------------------------------------
-// Each lane owns two adjacent columns (one float4): a slot's row is 128 bytes = all 32 banks, conflict-free.
 template <int RA_NS>
 __global__ void __launch_bounds__(RA_C * RA_NS, RA_NS == 64 ? 3 : 2) rotapply_kernel(const float2* __restrict__ Xall, int r,
                                                                  const float2* __restrict__ csall,
@@ -919,7 +921,7 @@ __global__ void __launch_bounds__(RA_C * RA_NS, RA_NS == 64 ? 3 : 2) rotapply_ke
 // =====================================================================================================================
 // Fixed small rank (compressionrank <= TK_MAXK): only the k leading eigenpairs are needed, so after the
 // tridiagonalisation the QL iteration, the reflector accumulation and the rotation application are replaced by
-//   (a) Sturm bisection for the k+1 largest eigenvalues of T (one thread per eigenvalue),
+//   (a) Sturm bisection for the k+1 largest eigenvalues of T (eight lanes per eigenvalue, three bits per round),
 //   (b) one twisted factorisation per eigenvalue for its eigenvector of T, then modified Gram-Schmidt,
 //   (c) the reflectors applied to those k vectors only.
 // Close eigenvalues only mix their own vectors (angle ~ eps / gap), which Gram-Schmidt keeps orthonormal and which
