@@ -350,6 +350,7 @@ int vk_destroy(vk_handle h) {
         if (e) cudaEventDestroy(e);
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
     for (auto& e : h->host_ev)
         if (e) cudaEventDestroy(e);
     delete h;
@@ -541,6 +542,7 @@ int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_
     // under the factorisation of sub-batch i (the factorisation polls the device, i.e. blocks this host thread, which is
     // why the copies are queued up front). Factors return on the copy stream as soon as their sub-batch is done.
     if (!h->copy_stream) VK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream2) VK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking));
     for (auto& e : h->host_ev)
         if (!e) VK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // only large batches are split: a sub-batch must still fill the GPU for the whole Jacobi iteration (measured: four
@@ -566,8 +568,9 @@ int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_
                                  static_cast<char*>(dV) + (size_t)b0 * kmax * n * 8, dR + b0, dT + (size_t)b0 * 4, nullptr, 0);
         if (rc) return rc;
         VK_CUDA(h, cudaEventRecord(h->host_ev[VK_HOST_CHUNKS + i], h->stream));
-        VK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->host_ev[VK_HOST_CHUNKS + i], 0));
-        cudaStream_t cs = h->copy_stream;
+        // factors come down on a second copy stream: under the uploads still queued on the first one (full duplex)
+        VK_CUDA(h, cudaStreamWaitEvent(h->copy_stream2, h->host_ev[VK_HOST_CHUNKS + i], 0));
+        cudaStream_t cs = h->copy_stream2;
         VK_CUDA(h, cudaMemcpyAsync(static_cast<char*>(U) + (size_t)b0 * m * kmax * 8, static_cast<char*>(dU) + (size_t)b0 * m * kmax * 8,
                                    (size_t)nb * m * kmax * 8, cudaMemcpyDeviceToHost, cs));
         VK_CUDA(h, cudaMemcpyAsync(S + (size_t)b0 * kmax, dS + (size_t)b0 * kmax, (size_t)nb * kmax * 4, cudaMemcpyDeviceToHost, cs));
@@ -577,6 +580,7 @@ int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_
         VK_CUDA(h, cudaMemcpyAsync(stats + (size_t)b0 * 4, dT + (size_t)b0 * 4, (size_t)nb * 16, cudaMemcpyDeviceToHost, cs));
     }
     VK_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    VK_CUDA(h, cudaStreamSynchronize(h->copy_stream2));
     VK_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int b = 0; b < B; ++b)
         if (stats[4 * b + 3] == 0.f)
@@ -602,17 +606,31 @@ int vk_reconstruct_host(vk_handle h, const void* U, const float* S, const void* 
     float* dS = reinterpret_cast<float*>(p + bO + bU);
     void* dV = p + bO + bU + bS;
     int32_t* dR = reinterpret_cast<int32_t*>(p + bO + bU + bS + bV);
-    VK_CUDA(h, cudaMemcpyAsync(dU, U, (size_t)B * m * kmax * 8, cudaMemcpyHostToDevice, h->stream));
-    VK_CUDA(h, cudaMemcpyAsync(dS, S, (size_t)B * kmax * 4, cudaMemcpyHostToDevice, h->stream));
-    VK_CUDA(h, cudaMemcpyAsync(dV, Vt, (size_t)B * kmax * n * 8, cudaMemcpyHostToDevice, h->stream));
-    if (ranks) VK_CUDA(h, cudaMemcpyAsync(dR, ranks, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
-    // sub-batches: the D2H copy of sub-batch i (copy stream) runs under the reconstruction of sub-batch i+1
+    // sub-batches with the two copy directions on their own streams: the factors of sub-batch i+1 go up (copy stream 2)
+    // while sub-batch i is reconstructed and the matrices of sub-batch i-1 come down (copy stream 1) - PCIe is full
+    // duplex, and with large ranks the factors are as big as the matrices (MeerKAT shard: 15.8 GB up, 17.4 GB down)
     if (!h->copy_stream) VK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (!h->copy_stream2) VK_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking));
     for (auto& e : h->host_ev)
         if (!e) VK_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const int nch = B < VK_HOST_CHUNKS ? B : VK_HOST_CHUNKS;
+    VK_CUDA(h, cudaEventRecord(h->host_ev[2 * VK_HOST_CHUNKS], h->stream));  // staging buffers are free again
+    VK_CUDA(h, cudaStreamWaitEvent(h->copy_stream2, h->host_ev[2 * VK_HOST_CHUNKS], 0));
+    VK_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->host_ev[2 * VK_HOST_CHUNKS], 0));
     for (int i = 0; i < nch; ++i) {
         const int b0 = (int)((long long)B * i / nch), b1 = (int)((long long)B * (i + 1) / nch), nb = b1 - b0;
+        cudaStream_t up = h->copy_stream2;
+        VK_CUDA(h, cudaMemcpyAsync(static_cast<char*>(dU) + (size_t)b0 * m * kmax * 8, static_cast<const char*>(U) + (size_t)b0 * m * kmax * 8,
+                                   (size_t)nb * m * kmax * 8, cudaMemcpyHostToDevice, up));
+        VK_CUDA(h, cudaMemcpyAsync(dS + (size_t)b0 * kmax, S + (size_t)b0 * kmax, (size_t)nb * kmax * 4, cudaMemcpyHostToDevice, up));
+        VK_CUDA(h, cudaMemcpyAsync(static_cast<char*>(dV) + (size_t)b0 * kmax * n * 8, static_cast<const char*>(Vt) + (size_t)b0 * kmax * n * 8,
+                                   (size_t)nb * kmax * n * 8, cudaMemcpyHostToDevice, up));
+        if (ranks) VK_CUDA(h, cudaMemcpyAsync(dR + b0, ranks + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, up));
+        VK_CUDA(h, cudaEventRecord(h->host_ev[VK_HOST_CHUNKS + i], up));
+    }
+    for (int i = 0; i < nch; ++i) {
+        const int b0 = (int)((long long)B * i / nch), b1 = (int)((long long)B * (i + 1) / nch), nb = b1 - b0;
+        VK_CUDA(h, cudaStreamWaitEvent(h->stream, h->host_ev[VK_HOST_CHUNKS + i], 0));
         rc = vk_reconstruct_batched(h, static_cast<char*>(dU) + (size_t)b0 * m * kmax * 8, dS + (size_t)b0 * kmax,
                                     static_cast<char*>(dV) + (size_t)b0 * kmax * n * 8, ranks ? dR + b0 : nullptr, nb, m, n, kmax,
                                     static_cast<char*>(dO) + (size_t)b0 * m * n * 8);
@@ -622,6 +640,7 @@ int vk_reconstruct_host(vk_handle h, const void* U, const float* S, const void* 
         VK_CUDA(h, cudaMemcpyAsync(static_cast<char*>(out) + (size_t)b0 * m * n * 8, static_cast<char*>(dO) + (size_t)b0 * m * n * 8,
                                    (size_t)nb * m * n * 8, cudaMemcpyDeviceToHost, h->copy_stream));
     }
+    VK_CUDA(h, cudaStreamSynchronize(h->copy_stream2));
     VK_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     VK_CUDA(h, cudaStreamSynchronize(h->stream));
     return VK_OK;

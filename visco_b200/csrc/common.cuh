@@ -34,6 +34,7 @@ struct vk_context {
     cudaEvent_t sub_ev[VK_MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream2 = nullptr;  // host-to-device direction of vk_reconstruct_host
     cudaEvent_t host_ev[2 * VK_HOST_CHUNKS + 1] = {};
     int stage_timing = 0;
     int chunk = 0;  // matrices per internal pass, 0 = auto
