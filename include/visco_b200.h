@@ -65,7 +65,9 @@ int vk_sync(vk_handle h);
  *          (default), 0 = shared-memory round-robin kernel only),
  *          "eig_impl" (Hermitian eigensolver of the Gram path: 0 = auto = 2 where min(m, n) <= 1024, 1 = one-sided cyclic
  *          Jacobi, 2 = Householder tridiagonalisation + implicit QL; with 0/2 a fixed rank <= 32 takes only the leading
- *          eigenpairs: Sturm bisection + twisted factorisation, unless "topk" = 1),
+ *          eigenpairs: Sturm bisection + twisted factorisation, unless "topk" = 1; "topk" = 2 extends that to the energy
+ *          rule: all eigenvalues by bisection, the rank estimated on the device, leading pairs per matrix where that
+ *          rank is <= 30 - pays on high-SNR data where most matrices qualify),
  *          "illcond_thr" (default 0.005: a matrix whose smallest retained singular value is below that * sigma_1 cannot be
  *          resolved through the float32 Gram matrix and is done again by one-sided Jacobi on the matrix itself; 0 = never),
  *          "ql_maxit" (QL iterations per eigenvalue before the pass is handed to the Jacobi solver, default 60). */

@@ -474,11 +474,11 @@ def test_direct_solver_hands_unconverged_passes_to_jacobi(eng, torch):
     """The QL iteration is limited per eigenvalue like LAPACK's; a matrix that hits the limit sends its pass back
     through the cyclic Jacobi solver. Forced here with a limit of one iteration."""
     A = _device_cube(eng, torch, 2, 4, 160, 320)
-    base = eng.compress(A, decorrelation=0.95)
+    base = eng.compress(A)                            # full rank: every matrix takes the QL iteration
     assert float(base[4][:, 2].min()) > 100          # QL iterations: the direct solver ran
     try:
         eng.set_option("ql_maxit", 1)
-        got = eng.compress(A, decorrelation=0.95)
+        got = eng.compress(A)
     finally:
         eng.set_option("ql_maxit", 60)
     torch.cuda.synchronize()
@@ -529,3 +529,25 @@ def test_odd_row_count_with_large_rank(eng, torch):
         for b in range(2):
             parity.check_factors(Ah[b], Uh[b], Sh[b], Vh[b], k, compressionrank=k, label=f"{m}x{n} k={k}")
             parity.check_reconstruction(Uh[b], Sh[b], Vh[b], oh[b], label=f"{m}x{n} k={k}")
+
+
+def test_energy_rule_through_the_leading_pair_path(eng, torch):
+    """Option topk = 2: with the energy rule the rank is estimated on the device from all eigenvalues (bisection) and
+    matrices that end up with a small rank take the leading-eigenpair path with their own k. Same ranks and factors as
+    the full QL path; matrices with a large rank (the noise-dominated cross hands) keep the full path."""
+    A = _device_cube(eng, torch, 6, 4, 192, 640)
+    base = eng.compress(A, decorrelation=0.9)
+    try:
+        eng.set_option("topk", 2)
+        got = eng.compress(A, decorrelation=0.9)
+    finally:
+        eng.set_option("topk", 0)
+    torch.cuda.synchronize()
+    st = got[4].cpu().numpy()
+    assert np.all(st[:, 3] == 1)
+    assert (st[:, 2] == 0).sum() >= 6 and (st[:, 2] > 0).sum() >= 6      # both routes were taken
+    assert torch.equal(got[3], base[3])
+    Ah, Uh, Sh, Vh, rk = (x.cpu().numpy() for x in (A, got[0], got[1], got[2], got[3]))
+    for b in range(A.shape[0]):
+        k = int(rk[b])
+        parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, decorrelation=0.9, label=f"energy topk=2 b={b}")

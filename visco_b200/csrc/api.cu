@@ -182,7 +182,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
         // fixed small rank: blocked subspace iteration first; the full Jacobi solver only sees what it left unsolved
         const bool qr = use_qr(h, m, n, fixed_rank) && !force_jacobi;
         if (qr) {
-            if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done, fixed_rank))) return rc;
+            if ((rc = vk_launch_eigqr(h, W, B, r, p.ld, ws + L.eig, sweeps, done, fixed_rank, decorrelation))) return rc;
         } else {
             const bool fast = h->topk != 1 && vk_topk_supported(r, fixed_rank, h->topk == 2);
             if (fast && (rc = vk_launch_topk(h, W, B, r, fixed_rank, done, sweeps))) return rc;

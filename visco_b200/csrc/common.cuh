@@ -120,7 +120,7 @@ int vk_launch_jacobi(vk_context* h, float2* W, int B, const JacobiPlan& p, int32
 bool vk_eigqr_supported(int r);
 size_t vk_eigqr_scratch_bytes(int B, int r);
 int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
-                    int32_t* done_dev, int fixed_rank = 0);
+                    int32_t* done_dev, int fixed_rank = 0, double decorrelation = 0.0);
 bool vk_topk_supported(int r, int fixed_rank, bool force);
 int vk_launch_topk(vk_context* h, float2* W, int B, int r, int fixed_rank, int32_t* done_dev, int32_t* sweeps_dev);
 

@@ -1005,13 +1005,79 @@ __global__ void __launch_bounds__(8 * (TK_MAXK + 1) + 24) bisect_kernel(int r, i
     }
 }
 
+// Energy rule with a small resulting rank: every eigenvalue by plain bisection (one thread each), then the rank the
+// selection stage will find, estimated from the same eigenvalues: kvec[b] = that rank + 2 (ties may move it by one),
+// flag[b] = 1 when the leading-pair path can deliver that many vectors.
+__global__ void __launch_bounds__(1024) bisect_all_kernel(int r, double energy, int klimit, const float* __restrict__ dall,
+                                                          const float* __restrict__ eall, float* __restrict__ lamall,
+                                                          float* __restrict__ lamtop, int32_t* __restrict__ kvec,
+                                                          int32_t* __restrict__ flag) {
+    extern __shared__ float bs_sm[];
+    float* d = bs_sm;
+    float* e2 = bs_sm + r;
+    float* lam = bs_sm + 2 * r;
+    __shared__ float s_lo[32], s_hi[32];
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    float lo = 3.4e38f, hi = -3.4e38f;
+    for (int i = tid; i < r; i += nthr) {
+        const float di = dall[(size_t)b * r + i];
+        const float ei = i < r - 1 ? eall[(size_t)b * r + i] : 0.f;
+        const float ep = i > 0 ? eall[(size_t)b * r + i - 1] : 0.f;
+        d[i] = di;
+        e2[i] = ei * ei;
+        const float rad = fabsf(ei) + fabsf(ep);
+        lo = fminf(lo, di - rad);
+        hi = fmaxf(hi, di + rad);
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    if (lane == 0) s_lo[tid >> 5] = lo, s_hi[tid >> 5] = hi;
+    __syncthreads();
+    for (int w = 0; w < (nthr + 31) / 32; ++w) lo = fminf(lo, s_lo[w]), hi = fmaxf(hi, s_hi[w]);
+    const float scale = fmaxf(fabsf(lo), fabsf(hi));
+    const float pivmin = fmaxf(1e-30f, 1e-14f * scale * scale);
+    for (int t = tid; t < r; t += nthr) {
+        const int idx = r - 1 - t;  // t-th largest
+        float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+        for (int it = 0; it < 48; ++it) {
+            const float mid = 0.5f * (a + c);
+            if (!(mid > a && mid < c)) break;
+            if (sturm_count(d, e2, r, mid, pivmin) > idx) c = mid;
+            else a = mid;
+        }
+        const float l = 0.5f * (a + c);
+        lam[t] = l;
+        lamall[(size_t)b * r + t] = l;
+        if (t <= TK_MAXK) lamtop[(size_t)b * (TK_MAXK + 1) + t] = l;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int t = 0; t < r; ++t) tot += fmax((double)lam[t], 0.0);
+        const double thr = energy * tot;
+        double cum = 0.0;
+        int k = r;
+        for (int t = 0; t < r; ++t) {
+            cum += fmax((double)lam[t], 0.0);
+            if (cum >= thr) {
+                k = t + 1;
+                break;
+            }
+        }
+        const int kv = k + 2;
+        kvec[b] = kv < r ? kv : r;
+        flag[b] = (lam[0] > 0.f && kv <= klimit && kv <= r - 2) ? 1 : 0;
+    }
+}
+
 // eigenvectors of T by twisted factorisation (one lane per eigenvalue), then modified Gram-Schmidt over the k vectors
-__global__ void __launch_bounds__(32) twisted_kernel(int r, int k, const float* __restrict__ dall,
-                                                     const float* __restrict__ eall, const float* __restrict__ lamtop,
-                                                     int32_t* __restrict__ flag, float* __restrict__ zall,
-                                                     float* __restrict__ dmall) {
+__global__ void __launch_bounds__(32) twisted_kernel(int r, int kuni, const int32_t* __restrict__ kvec,
+                                                     const float* __restrict__ dall, const float* __restrict__ eall,
+                                                     const float* __restrict__ lamtop, int32_t* __restrict__ flag,
+                                                     float* __restrict__ zall, float* __restrict__ dmall) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (flag[b] == 0) return;
+    const int k = kvec ? kvec[b] : kuni;  // energy rule: per matrix
     const float* d = dall + (size_t)b * r;
     const float* e = eall + (size_t)b * r;
     float* zb = zall + (size_t)b * TK_MAXK * r;
@@ -1098,14 +1164,16 @@ __global__ void __launch_bounds__(32) twisted_kernel(int r, int k, const float* 
 // W[t][:] = lambda_t conj(v_t) for t < k and zero rows below: what the selection and factor stages expect.
 template <int EPL, int RPW>
 __global__ void __launch_bounds__(FQ_THREADS, (EPL * RPW <= 32) ? 2 : 1)
-    backtr_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, int k, const float* __restrict__ tauall,
-                  const float2* __restrict__ phall, const float* __restrict__ zall, const float* __restrict__ lamtop,
-                  const int32_t* __restrict__ flag, int32_t* __restrict__ done, int32_t* __restrict__ sweeps) {
+    backtr_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, int kuni, const int32_t* __restrict__ kvec,
+                  const float* __restrict__ lamall, const float* __restrict__ tauall, const float2* __restrict__ phall,
+                  const float* __restrict__ zall, const float* __restrict__ lamtop, const int32_t* __restrict__ flag,
+                  int32_t* __restrict__ done, int32_t* __restrict__ sweeps) {
     constexpr int WIDTH = EPL * 32;
     extern __shared__ float2 fq_sv[];  // [FQ_TJ][WIDTH]
     __shared__ float stau[FQ_TJ];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (flag[b] == 0) return;
+    const int k = kvec ? kvec[b] : kuni;
     float2* M = Wall + (size_t)b * wstride;
     const float* taus = tauall + (size_t)b * r;
     const int i0 = warp * RPW;
@@ -1177,9 +1245,10 @@ __global__ void __launch_bounds__(FQ_THREADS, (EPL * RPW <= 32) ? 2 : 1)
             if (kk < r) M[(size_t)t * ld + kk] = make_float2(lam * y[q][e].x, -lam * y[q][e].y);
         }
     }
+    // rows below: zero, or (energy rule: the selection stage needs every eigenvalue) a vector of norm lambda_row
     for (int idx = tid; idx < (r - k) * r; idx += FQ_THREADS) {
         const int row = k + idx / r, kk = idx % r;
-        M[(size_t)row * ld + kk] = make_float2(0.f, 0.f);
+        M[(size_t)row * ld + kk] = make_float2((lamall && kk == 0) ? lamall[(size_t)b * r + row] : 0.f, 0.f);
     }
     if (tid == 0) {
         done[b] = 1;
@@ -1190,7 +1259,7 @@ __global__ void __launch_bounds__(FQ_THREADS, (EPL * RPW <= 32) ? 2 : 1)
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct EigScratch {
-    size_t X, d, e, tau, ph, lam, cs, sw, meta, lamtop, flag, z, dm, total;
+    size_t X, d, e, tau, ph, lam, cs, sw, meta, lamtop, flag, kvec, z, dm, total;
     int cap, scap, lcap;
 };
 
@@ -1211,6 +1280,7 @@ EigScratch eig_layout(int B, int r) {
     s.meta = off, off += al((size_t)B * 16);
     s.lamtop = off, off += al((size_t)B * (TK_MAXK + 1) * 4);
     s.flag = off, off += al((size_t)B * 4);
+    s.kvec = off, off += al((size_t)B * 4);
     s.z = off, off += al((size_t)B * TK_MAXK * r * 4);
     s.dm = off, off += al((size_t)B * TK_MAXK * r * 4);
     s.total = off;
@@ -1278,10 +1348,11 @@ int launch_rotapply(vk_context* h, cudaStream_t st, const float2* X, int B, int 
 
 template <int EPL, int RPW>
 int launch_backtr(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, int k, const float* tau,
-                  const float2* ph, const EigScratch& L, unsigned char* sc, int32_t* done, int32_t* sweeps) {
+                  const float2* ph, const EigScratch& L, unsigned char* sc, int32_t* done, int32_t* sweeps,
+                  const int32_t* kvec = nullptr, const float* lamall = nullptr) {
     const size_t smem = (size_t)FQ_TJ * EPL * 32 * sizeof(float2);
     VK_CUDA(h, cudaFuncSetAttribute(backtr_kernel<EPL, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    backtr_kernel<EPL, RPW><<<B, FQ_THREADS, smem, st>>>(W, r, ld, wstride, k, tau, ph,
+    backtr_kernel<EPL, RPW><<<B, FQ_THREADS, smem, st>>>(W, r, ld, wstride, k, kvec, lamall, tau, ph,
                                                          reinterpret_cast<const float*>(sc + L.z),
                                                          reinterpret_cast<const float*>(sc + L.lamtop),
                                                          reinterpret_cast<const int32_t*>(sc + L.flag), done, sweeps);
@@ -1308,7 +1379,7 @@ size_t vk_eigqr_scratch_bytes(int B, int r) { return eig_layout(B, r).total; }
 // fixed_rank > 0 (and small enough): only the leading fixed_rank vectors are produced for matrices whose leading
 // eigenvalues are well separated (rows below are zero); the others take the full path.
 int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
-                    int32_t* done_dev, int fixed_rank) {
+                    int32_t* done_dev, int fixed_rank, double decorrelation) {
     if (B <= 0) return VK_OK;
     if (!vk_eigqr_supported(r)) return vk_fail(h, VK_EINVAL, "eig_impl=2 does not support this size");
     const EigScratch L = eig_layout(B, r);
@@ -1345,7 +1416,7 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         bisect_kernel<<<B, (8 * (k + 1) + 31) / 32 * 32, (size_t)2 * r * 4, st>>>(r, k + 1, d, e, lamtop, flag,
                                                                                 TK_GAP);
         VK_LAUNCH_CHECK(h);
-        twisted_kernel<<<B, 32, 0, st>>>(r, k, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
+        twisted_kernel<<<B, 32, 0, st>>>(r, k, nullptr, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
                                          reinterpret_cast<float*>(sc + L.dm));
         VK_LAUNCH_CHECK(h);
         // vectors per warp: as few as the eight warps of the CTA allow (k <= 8: one each)
@@ -1362,6 +1433,30 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
 #undef VK_BACKTR
         if (rc) return rc;
         skip = flag;  // the full path below takes what is left (flag 0)
+    } else if (h->topk == 2 && fixed_rank <= 0 && decorrelation > 0.0 && decorrelation < 1.0 && r >= 8) {
+        // (opt-in: pays when most matrices of the batch end up with a small rank - high SNR data; one matrix that needs the
+        // full path brings the latency of the QL kernel back, and the extra bisection costs 1-5 % when none qualifies)
+        // energy rule: all eigenvalues by bisection; matrices whose rank (+2) is within reach take the leading-pair
+        // path with their own k and leave the remaining eigenvalues as dummy rows for the selection stage
+        float* lamtop = reinterpret_cast<float*>(sc + L.lamtop);
+        float* lamall = reinterpret_cast<float*>(sc + L.lam);
+        int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
+        int32_t* kvec = reinterpret_cast<int32_t*>(sc + L.kvec);
+        const int klimit = topk_qr_limit(r);
+        const int nthr = r >= 1024 ? 1024 : (r + 31) / 32 * 32;
+        bisect_all_kernel<<<B, nthr, (size_t)3 * r * 4, st>>>(r, decorrelation * decorrelation, klimit, d, e, lamall, lamtop,
+                                                             kvec, flag);
+        VK_LAUNCH_CHECK(h);
+        twisted_kernel<<<B, 32, 0, st>>>(r, 0, kvec, d, e, lamtop, flag, reinterpret_cast<float*>(sc + L.z),
+                                         reinterpret_cast<float*>(sc + L.dm));
+        VK_LAUNCH_CHECK(h);
+        if (r <= 64) rc = launch_backtr<2, 4>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
+        else if (r <= 128) rc = launch_backtr<4, 4>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
+        else if (r <= 256) rc = launch_backtr<8, 4>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
+        else if (r <= 512) rc = launch_backtr<16, 4>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
+        else rc = launch_backtr<32, 2>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
+        if (rc) return rc;
+        skip = flag;
     }
     if (dbg) cudaEventRecord(ev[2], st);
     // the scalar QL iteration is latency bound (one lane per matrix): it runs alone - sharing the SMs with another
