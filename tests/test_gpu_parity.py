@@ -551,3 +551,20 @@ def test_energy_rule_through_the_leading_pair_path(eng, torch):
     for b in range(A.shape[0]):
         k = int(rk[b])
         parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, decorrelation=0.9, label=f"energy topk=2 b={b}")
+
+
+def test_stage_and_kernel_timers_of_the_c_abi(eng, torch):
+    """vk_last_stage_ms / vk_last_eig_ms (option stage_timing = 1): the slots add up and name the kernels that ran."""
+    A = _device_cube(eng, torch, 4, 4, 256, 512)
+    try:
+        eng.set_option("stage_timing", 1)
+        eng.compress(A, compressionrank=4)
+        st, eig = eng.last_stage_ms(), eng.last_eig_ms()
+        assert st["gram"] > 0 and st["jacobi"] > 0 and st["factors"] > 0 and st["total"] >= st["jacobi"]
+        assert eig["tridiag"] > 0 and eig["leading_pairs"] > 0               # fixed small rank: leading eigenpairs
+        assert abs(sum(eig.values()) - st["jacobi"]) <= 0.2 * st["jacobi"] + 0.05
+        eng.compress(A, decorrelation=0.99)
+        eig = eng.last_eig_ms()
+        assert eig["ql"] > 0 and eig["reflectors"] > 0 and eig["rotations"] > 0   # energy rule: the full QL route
+    finally:
+        eng.set_option("stage_timing", 0)
