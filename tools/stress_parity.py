@@ -33,6 +33,7 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     eig_impl = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     only = int(sys.argv[4]) if len(sys.argv) > 4 else -1   # run this case only (the random stream is kept in step)
+    maxdim = int(sys.argv[5]) if len(sys.argv) > 5 else 700  # upper size of the 'big' cases (1024 < r uses the Jacobi solver)
     rng = np.random.default_rng(seed)
     eng = get_engine(0)
     eng.set_option("eig_impl", eig_impl)
@@ -40,8 +41,8 @@ def main():
     fails = 0
     for case in range(ncases):
         big = rng.random() < 0.2
-        m = int(rng.integers(2, 700 if big else 200))
-        n = int(rng.integers(2, 700 if big else 300))
+        m = int(rng.integers(2, maxdim if big else 200))
+        n = int(rng.integers(2, maxdim if big else 300))
         r = min(m, n)
         mode = rng.choice(["fixed", "energy", "full"], p=[0.5, 0.35, 0.15])
         kw = {}
