@@ -25,7 +25,8 @@
  *   Vt   [B][kmax][n]   complex64   rows >= ranks[b] are zero      (the reference calls it Vt / WT)
  *   ranks[B]            int32
  *   stats[B][4]         float32     { ||A||_F^2 (sum of all sigma^2), retained energy (sum of kept sigma^2),
- *                                     Jacobi sweeps used, converged flag (1/0) }
+ *                                     eigensolver iterations (QL iterations, or Jacobi sweeps; 0 when only the
+ *                                     leading eigenpairs were computed), converged flag (1/0) }
  */
 #ifndef VISCO_B200_H
 #define VISCO_B200_H
@@ -59,8 +60,9 @@ int vk_sync(vk_handle h);
  *          "gram_impl" (0 = auto: tcgen05 where the shape allows, 1 = force SIMT fp32, 2 = force tcgen05),
  *          "check_finite" (default 1), "check_every" (host convergence poll period in sweeps, default 1),
  *          "jacobi_bsz" (vectors per block, 0 = auto), "jacobi_groups" (concurrent matrix groups, 0 = auto), "chunk" (matrices per internal pass, 0 = auto),
- *          "stage_timing" (0/1, see vk_last_stage_ms), "topk" (0 = blocked subspace iteration for fixed rank <= 4 with
- *          fallback to the full solver, 1 = full solver only, 2 = also for ranks up to 8), "gemm_impl" (0 = tcgen05 GEMM for k > 8, 1 = SIMT),
+ *          "stage_timing" (0/1, see vk_last_stage_ms), "topk" (shortcuts for small ranks: 0 = auto, 1 = none, 2 = extended; what they
+ *          are depends on "eig_impl", see there; with the Jacobi solver: blocked subspace iteration for fixed rank <= 4 / <= 8
+ *          with per-matrix fallback to the full solver), "gemm_impl" (0 = tcgen05 GEMM for k > 8, 1 = SIMT),
  *          "small_reg" (1 = register-resident recursive-tournament kernel on the small path where the shape allows
  *          (default), 0 = shared-memory round-robin kernel only),
  *          "eig_impl" (Hermitian eigensolver of the Gram path: 0 = auto = 2 where min(m, n) <= 1024, 1 = one-sided cyclic

@@ -229,16 +229,13 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
 // vectors streamed from global memory - in sub-batches gathered into a second workspace, and their results replace the
 // first ones. One 4-byte poll per call when nothing is flagged.
 int redo_ill_conditioned(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation,
-                         int kmax, float2* U, float* S, float2* Vt, int32_t* ranks, float* stats, unsigned char* ws,
-                         const WsLayout& L) {
+                         int kmax, float2* U, float* S, float2* Vt, int32_t* ranks, float* stats) {
     int rc;
-    // flags live behind the per-chunk bookkeeping of the main workspace: reuse perm (chunk * r ints >= B? not always)
+    // the flags (and everything else of this path) live in a second workspace: the first is sized per internal pass
     const size_t fbytes = align_up((size_t)B * 4) + 256;
     if ((rc = ensure(h, &h->ws2, &h->ws2_bytes, fbytes))) return rc;
     int32_t* flags = static_cast<int32_t*>(h->ws2);
     int32_t* count = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(h->ws2) + align_up((size_t)B * 4));
-    (void)ws;
-    (void)L;
     if ((rc = vk_launch_flag_illcond(h, S, ranks, B, kmax, h->illcond_thr, flags, count))) return rc;
     VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 3, count, 4, cudaMemcpyDeviceToHost, h->stream));
     VK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -489,7 +486,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
         }
     }
     if (gram_path && h->illcond_thr > 0.f) {
-        rc = redo_ill_conditioned(h, Ap, B, m, n, fixed_rank, decorrelation, kmax, Up, S, Vp, ranks, stats, wsp, L);
+        rc = redo_ill_conditioned(h, Ap, B, m, n, fixed_rank, decorrelation, kmax, Up, S, Vp, ranks, stats);
         if (rc) return rc;
     }
     if (h->stage_timing) {
