@@ -514,7 +514,8 @@ def test_ill_conditioned_matrices_are_redone_without_a_gram_product(eng, torch):
     finally:
         eng.set_option("illcond_thr", 0.005)
     U1, S1, Vt1, r1, _ = eng.compress(Ad, compressionrank=5)
-    assert torch.equal(S0, S1) and torch.equal(r0, r1)
+    # (not bit-identical from call to call: the refined singular values are accumulated with atomics)
+    assert torch.equal(r0, r1) and float(((S0 - S1).abs() / S0.clamp_min(1e-20)).max()) < 2e-6
 
 
 def test_odd_row_count_with_large_rank(eng, torch):
