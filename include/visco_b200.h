@@ -136,6 +136,12 @@ int vk_gather_baselines(vk_handle h, const void* data_dev, int nchan, int ncorr,
 int vk_scatter_baselines(vk_handle h, const void* cube_dev, int nchan, int ncorr, const int32_t* row_idx_dev, int nbl,
                          int m, const int32_t* corr_sel_dev, int ncs, int stack, void* data_dev);
 
+/* Validates the index arrays of the two calls above before they are used: entries of row_idx outside [-1, nrow) and
+ * entries of corr_sel outside [0, ncorr) are counted into *bad_host (synchronous). Returns VK_EINVAL when any is found
+ * (the reference's numpy indexing raises IndexError there, decompress_ms.py:216-232). */
+int vk_check_layout_indices(vk_handle h, const int32_t* row_idx_dev, size_t nrow_idx, int nrow,
+                            const int32_t* corr_sel_dev, size_t ncorr_sel, int ncorr, int32_t* bad_host);
+
 /* ---- flags ---------------------------------------------------------------------------------- */
 /* np.packbits(flags, axis=None) / np.unpackbits(packed, count=n) on device, big bit order (compress_ms.py:478-483,
  * decompress_ms.py:240-246). flags are one byte per element (numpy bool). packed has (n + 7) / 8 bytes. */

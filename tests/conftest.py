@@ -21,3 +21,26 @@ def golden():
 @pytest.fixture(scope="session")
 def golden_cases(golden):
     return sorted({k.split("/")[0] for k in golden.files if "/" in k})
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Worst raw ratios against the bare north-star tolerances (tests/parity.py REPORT), printed and saved."""
+    try:
+        from tests import parity
+    except Exception:
+        return
+    if not parity.REPORT:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(parity.REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    worst = {}
+    for slot in parity.REPORT.values():
+        for k, v in slot.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+    print("\n[parity] worst raw ratios vs bare north-star tolerances:", json.dumps(worst))

@@ -1,11 +1,15 @@
 """Shared parity checks: CUDA path vs the oracle, with the tolerances BASELINE.json's north_star states.
 
   retained singular values : |S - S_ref| <= 1e-4 * S_ref              (+ 2e-6 * S_ref[0] absolute floor: fp32 noise)
-  reconstruction error     : | ||A - A_hat|| - ||A - A_ref|| | <= 1e-5 * ||A - A_ref||   (+ 5e-6 * ||A|| floor, for
-                             exactly-low-rank inputs whose reference error is itself float32 round-off)
+  reconstruction error     : | ||A - A_hat|| - ||A - A_ref|| | <= 1e-5 * ||A - A_ref||   (a 5e-6 * ||A|| floor applies ONLY
+                             when the reference error is itself float32 round-off, ||A - A_ref|| < 1e-3 ||A||: full-rank
+                             and exactly-low-rank inputs)
   chosen rank              : identical, except when the cumulative energy at the smaller of the two ranks lies
                              within 2e-4 (relative, i.e. a 1e-4 change of one singular value) of the threshold
 Singular vectors are compared through reconstructions and orthonormality only (phase ambiguity).
+
+Every check also records its raw ratio against the BARE north-star tolerance (no floors) in REPORT; the session hook
+in tests/conftest.py prints the worst cases and writes them to gpurun_out/parity_report.json.
 """
 import numpy as np
 
@@ -16,6 +20,17 @@ S_FLOOR = 2e-6
 ERR_RTOL = 1e-5
 ERR_FLOOR = 5e-6
 TIE_RTOL = 2e-4
+ROUNDOFF_ERR = 1e-3      # reference error below this * ||A||: the reconstruction error is float32 round-off, not truncation
+
+REPORT = {}              # label prefix -> dict of worst raw ratios vs the bare tolerances
+
+
+def _record(label, **kv):
+    key = label.split(" b=")[0].split("/k")[0] if label else "unlabelled"
+    slot = REPORT.setdefault(key, {})
+    for k, v in kv.items():
+        if isinstance(v, (int, float)) and (k not in slot or v > slot[k]):
+            slot[k] = float(v)
 
 
 def rank_is_acceptable(s_ref, decorrelation, k, k_ref):
@@ -62,7 +77,12 @@ def check_factors(a, U, S, Vt, k, decorrelation=None, compressionrank=None, labe
     e_ref = np.linalg.norm(a64 - rec_ref)
     na = np.linalg.norm(a64)
     # float32 round-off of r accumulated plane rotations / reflectors grows like sqrt(r): the floor is stated at r = 256
-    floor = ERR_FLOOR * max(1.0, np.sqrt(min(a.shape) / 256.0))
+    roundoff = e_ref < ROUNDOFF_ERR * na
+    floor = ERR_FLOOR * max(1.0, np.sqrt(min(a.shape) / 256.0)) if roundoff else 0.0
+    _record(label, sigma_over_1e4=float((ds / np.maximum(s_ref_full[:kk].astype(np.float64), 1e-30)).max() / S_RTOL) if kk else 0.0,
+            **({"err_abs_over_normA_roundoff_cases": abs(e - e_ref) / max(na, 1e-30)} if roundoff else
+               {"err_over_1e5": abs(e - e_ref) / max(e_ref, 1e-30) / ERR_RTOL}),
+            rank_mismatch=float(k != k_ref))
     assert abs(e - e_ref) <= ERR_RTOL * e_ref + floor * na, (label, "recon err", e, e_ref, (e - e_ref) / max(e_ref, 1e-30))
     # orthonormal factors (only meaningful for modes above the float32 noise floor). The vectors on the smaller side of
     # the matrix come from the eigenvectors of the Gram matrix and are orthonormal throughout; the ones on the longer
@@ -91,4 +111,5 @@ def check_reconstruction(U, S, Vt, out, label=""):
     scale = max(float(np.abs(ref).max()), 1e-30)
     err = float(np.abs(out - ref).max())
     assert out.dtype == np.complex64 and out.shape == ref.shape, label
+    _record(label or "reconstruct", recon_maxabs_over_scale=err / scale)
     assert err <= 2e-5 * scale * max(1.0, np.sqrt(len(S))), (label, "reconstruct", err, scale)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "vk_gram_uses_tcgen05": (_i, [_i, _i, _i]),
     "vk_gather_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "vk_scatter_baselines": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "vk_check_layout_indices": (_i, [_vp, _vp, _sz, _i, _vp, _sz, _i, C.POINTER(C.c_int32)]),
     "vk_packbits": (_i, [_vp, _vp, _sz, _vp]),
     "vk_unpackbits": (_i, [_vp, _vp, _sz, _vp]),
     "vk_flag_replace": (_i, [_vp, _vp, _vp, _vp, _f, _f, _sz]),

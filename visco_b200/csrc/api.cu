@@ -323,6 +323,11 @@ int vk_create(vk_handle* out, int device) {
         return VK_ENOMEM;
     }
     std::memset(h->h_poll, 0, 64);
+    if (cudaMalloc(&h->d_scratch, 256) != cudaSuccess) {
+        cudaFreeHost(h->h_poll);
+        delete h;
+        return VK_ENOMEM;
+    }
     for (auto& e : h->ev) cudaEventCreate(&e);
     for (auto& e : h->eig_ev) cudaEventCreate(&e);
     *out = h;
@@ -337,6 +342,7 @@ int vk_destroy(vk_handle h) {
     if (h->stage) cudaFree(h->stage);
     if (h->ws2) cudaFree(h->ws2);
     if (h->h_poll) cudaFreeHost(h->h_poll);
+    if (h->d_scratch) cudaFree(h->d_scratch);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->eig_ev)

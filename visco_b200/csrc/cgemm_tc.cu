@@ -202,7 +202,15 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll 2
             for (int i = 0; i < (int)(A_BYTES / 16) / NUM_CONVERTERS; ++i) {
                 const int c = ct + i * NUM_CONVERTERS;
-                const Split4 sa = split4(a_hi[c]);
+                float4 av = a_hi[c];
+                if (MODE == MODE_RECON) {
+                    // columns of U at or beyond ranks[b] are not part of the product, whatever they hold (the last K-block
+                    // may reach past the rank): logical 16-byte chunk = physical chunk XOR (row & 7) under SWIZZLE_128B
+                    const int col = kb * KB_C + 2 * ((c & 7) ^ ((c >> 3) & 7));
+                    if (col >= Kvalid) av.x = av.y = 0.f;
+                    if (col + 1 >= Kvalid) av.z = av.w = 0.f;
+                }
+                const Split4 sa = split4(av);
                 a_hi[c] = sa.hi;
                 a_lo[c] = sa.lo;
             }
@@ -215,11 +223,15 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 float4 v = b_raw[c];
                 if (MODE == MODE_RECON) {
                     const int cc = kb * KB_C + t;
-                    const float sc = cc < g.kmax ? g.S[(size_t)b * g.kmax + cc] : 0.f;
-                    v.x *= sc;
-                    v.y *= sc;
-                    v.z *= sc;
-                    v.w *= sc;
+                    if (cc < Kvalid) {
+                        const float sc = g.S[(size_t)b * g.kmax + cc];
+                        v.x *= sc;
+                        v.y *= sc;
+                        v.z *= sc;
+                        v.w *= sc;
+                    } else {
+                        v = make_float4(0.f, 0.f, 0.f, 0.f);  // modes beyond ranks[b]: never read as data
+                    }
                 }
                 const Split4 s0 = split4(v);
                 const Split4 s1 = split4(rot90(v));

@@ -20,6 +20,7 @@ struct vk_context {
     void* stage = nullptr;  // grow-only device staging for the *_host entry points
     size_t stage_bytes = 0;
     int32_t* h_poll = nullptr;  // pinned host words the convergence loop copies into
+    void* d_scratch = nullptr;  // 256 bytes of device memory for counters of the small utility kernels
     int64_t launches = 0;
     int num_sms = 148;
     // options

@@ -36,6 +36,7 @@ layout_kernel(float2* __restrict__ data, const int32_t* __restrict__ row_idx, co
     for (int v = threadIdx.x; v < nchan; v += blockDim.x) {
         for (int j = 0; j < ncs; ++j) {
             const int c = corr_sel[(size_t)bl * ncs + j];  // per-baseline selection
+            if ((unsigned)c >= (unsigned)ncorr) continue;  // never touch memory outside the row (vk_check_layout_indices reports it)
             int b, tt;
             dest(bl, j, t, ncs, stack, m, b, tt);
             float2* q = cube + ((size_t)b * mm + tt) * nchan + v;
@@ -72,6 +73,23 @@ __global__ void __launch_bounds__(256) flag_replace_kernel(float2* __restrict__ 
                                                            const float2* __restrict__ model, float2 value, size_t n) {
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
         if (flags[e]) data[e] = model ? model[e] : value;
+}
+
+// number of entries of row_idx outside [-1, nrow) plus entries of corr_sel outside [0, ncorr)
+__global__ void __launch_bounds__(256) check_indices_kernel(const int32_t* __restrict__ row_idx, size_t nrow_idx, int nrow,
+                                                            const int32_t* __restrict__ corr_sel, size_t ncorr_sel, int ncorr,
+                                                            int32_t* __restrict__ bad) {
+    int c = 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nrow_idx; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = row_idx[e];
+        c += (r < -1 || r >= nrow);
+    }
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < ncorr_sel; e += (size_t)gridDim.x * blockDim.x) {
+        const int q = corr_sel[e];
+        c += (q < 0 || q >= ncorr);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(bad, c);
 }
 
 }  // namespace
@@ -134,6 +152,23 @@ int vk_flag_replace(vk_handle h, void* data_dev, const uint8_t* flags_dev, const
                                                              static_cast<const float2*>(model_dev),
                                                              make_float2(value_re, value_im), n);
     VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
+int vk_check_layout_indices(vk_handle h, const int32_t* row_idx_dev, size_t nrow_idx, int nrow,
+                            const int32_t* corr_sel_dev, size_t ncorr_sel, int ncorr, int32_t* bad_host) {
+    if (!h) return VK_EINVAL;
+    if (!row_idx_dev || !corr_sel_dev || !bad_host) return vk_fail(h, VK_EINVAL, "null buffer");
+    VK_CUDA(h, cudaSetDevice(h->device));
+    int32_t* cnt = reinterpret_cast<int32_t*>(h->d_scratch);
+    VK_CUDA(h, cudaMemsetAsync(cnt, 0, 4, h->stream));
+    check_indices_kernel<<<flag_grid(nrow_idx + ncorr_sel), 256, 0, h->stream>>>(row_idx_dev, nrow_idx, nrow, corr_sel_dev,
+                                                                               ncorr_sel, ncorr, cnt);
+    VK_LAUNCH_CHECK(h);
+    VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 8, cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+    VK_CUDA(h, cudaStreamSynchronize(h->stream));
+    *bad_host = h->h_poll[8];
+    if (*bad_host) return vk_fail(h, VK_EINVAL, std::to_string(*bad_host) + " row / correlation indices are out of range");
     return VK_OK;
 }
 

@@ -573,7 +573,8 @@ struct ReconOp {  // out[t][v] = sum_c (U[t][c] S[c]) Vt[c][v]
 template <int KC, int ROWS>
 __global__ void __launch_bounds__(128)
 recon_smallk_kernel(const float2* __restrict__ U, const float* __restrict__ S, const float2* __restrict__ Vt,
-                    float2* __restrict__ out, int m, int n, int kmax, int strips, int rsplit) {
+                    const int32_t* __restrict__ ranks, float2* __restrict__ out, int m, int n, int kmax, int strips,
+                    int rsplit) {
     __shared__ float4 us[ROWS * KC];
     int bid = blockIdx.x;
     const int rs = bid % rsplit;
@@ -582,11 +583,14 @@ recon_smallk_kernel(const float2* __restrict__ U, const float* __restrict__ S, c
     const int b = bid / strips;
     const int t0 = rs * ROWS;
     const int rows = min(ROWS, m - t0);
+    // only the first ranks[b] modes count (include/visco_b200.h): whatever sits beyond them is never read
+    int kr = kmax;
+    if (ranks) kr = min(max(ranks[b], 0), kmax);
     for (int e = threadIdx.x; e < rows * KC; e += 128) {
         const int t = e / KC, c = e - t * KC;
         float2 u = make_float2(0.f, 0.f);
         float s = 0.f;
-        if (c < kmax) {
+        if (c < kr) {
             u = U[((size_t)b * m + t0 + t) * kmax + c];
             s = S[(size_t)b * kmax + c];
         }
@@ -598,7 +602,7 @@ recon_smallk_kernel(const float2* __restrict__ U, const float* __restrict__ S, c
 #pragma unroll
     for (int c = 0; c < KC; ++c) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && c < kmax) v = *reinterpret_cast<const float4*>(Vt + ((size_t)b * kmax + c) * n + v0);
+        if (live && c < kr) v = *reinterpret_cast<const float4*>(Vt + ((size_t)b * kmax + c) * n + v0);
         va[c] = make_float2(v.x, v.y);
         vas[c] = make_float2(v.y, v.x);
         vb[c] = make_float2(v.z, v.w);
@@ -624,14 +628,14 @@ recon_smallk_kernel(const float2* __restrict__ U, const float* __restrict__ S, c
 }
 
 template <int KC>
-static int launch_recon_smallk(vk_context* h, const float2* U, const float* S, const float2* Vt, int B, int m, int n,
-                               int kmax, float2* out) {
+static int launch_recon_smallk(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks,
+                               int B, int m, int n, int kmax, float2* out) {
     constexpr int ROWS = 64;
     const int strips = (n + 255) / 256;
     const int rsplit = (m + ROWS - 1) / ROWS;
     const long long nblocks = (long long)B * strips * rsplit;
     if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "reconstruct: grid too large");
-    recon_smallk_kernel<KC, ROWS><<<(unsigned)nblocks, 128, 0, h->stream>>>(U, S, Vt, out, m, n, kmax, strips, rsplit);
+    recon_smallk_kernel<KC, ROWS><<<(unsigned)nblocks, 128, 0, h->stream>>>(U, S, Vt, ranks, out, m, n, kmax, strips, rsplit);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
@@ -891,14 +895,14 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
 
 int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
                           int m, int n, int kmax, float2* out) {
-    // small rank: dedicated streaming kernel (factors are zero-padded beyond ranks[b], so kmax modes are summed)
+    // small rank: dedicated streaming kernel (modes >= ranks[b] are skipped, as on the other two paths)
     const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
     // (k <= 16 stays below the FFMA2 limit of ~0.7 x HBM; the tcgen05 GEMM only wins from k ~ 20 on, measured)
     if (aligned && kmax <= 16 && !h->recon_generic) {
-        if (kmax <= 2) return launch_recon_smallk<2>(h, U, S, Vt, B, m, n, kmax, out);
-        if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, B, m, n, kmax, out);
-        if (kmax <= 8) return launch_recon_smallk<8>(h, U, S, Vt, B, m, n, kmax, out);
-        return launch_recon_smallk<16>(h, U, S, Vt, B, m, n, kmax, out);
+        if (kmax <= 2) return launch_recon_smallk<2>(h, U, S, Vt, ranks, B, m, n, kmax, out);
+        if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, ranks, B, m, n, kmax, out);
+        if (kmax <= 8) return launch_recon_smallk<8>(h, U, S, Vt, ranks, B, m, n, kmax, out);
+        return launch_recon_smallk<16>(h, U, S, Vt, ranks, B, m, n, kmax, out);
     }
     if (h->gemm_impl == 0 && kmax > 16 && vk_cgemm_tc_supported(m, n, kmax) &&
         ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0))

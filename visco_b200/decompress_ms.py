@@ -95,6 +95,31 @@ def _store_index(zarr_path):
     return ant1, ant2, rowid, names, shape
 
 
+def leaf_planes(zarr_path: str, ncorr: int) -> dict:
+    """Leaf directory name -> correlation plane(s) of the (row, chan, corr) column.
+
+    The compressor picks planes by looking the casacore enum up in POLARIZATION/CORR_TYPE (reference compress_ms.py:
+    601-602, 631-632, 662), so the decompressor does the same when the store carries that table: a 2-correlation
+    [XX, YY] column then gets its "YY" / "diagonals" leaves back in planes (1) / (0, 1). The reference's decompressor
+    hard-codes linear-feed positions instead (decompress_ms.py:182, 222-229: XX 0, XY 1, YX 2, YY -1, diagonals 0/3,
+    offdiagonals 1/2) - identical for the usual [9, 10, 11, 12] column, and used here when CORR_TYPE is absent."""
+    import os
+
+    from .msdata import CORR_TYPES
+    from .zarr_leaf import read_array
+    planes = {"XX": (0,), "XY": (1,), "YX": (2,), "YY": (ncorr - 1,), "diagonals": (0, 3), "offdiagonals": (1, 2)}
+    p = os.path.join(zarr_path, "POLARIZATION", "CORR_TYPE")
+    if os.path.isdir(p):
+        ct = [int(x) for x in np.asarray(read_array(p)).reshape(-1)[:ncorr]]
+        by_name = {name: (ct.index(enum),) for name, enum in CORR_TYPES.items() if enum in ct}
+        planes.update(by_name)
+        if 9 in ct and 12 in ct:
+            planes["diagonals"] = (ct.index(9), ct.index(12))
+        if 10 in ct and 11 in ct:
+            planes["offdiagonals"] = (ct.index(10), ct.index(11))
+    return planes
+
+
 def construct_main_ds(zarr_path: str, column: str, batch_size: int):
     """Rebuild the visibility column from the leaf tree (reference construct_main_ds, decompress_ms.py:134-234).
 
@@ -133,8 +158,7 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
             raise ValueError(f"{zarr_path} holds no factor leaves under MAIN/{column}")
         shape = [len(ant1), nchan, 4]
     ncorr = int(shape[2])
-    planes = {"XX": (0,), "XY": (1,), "YX": (2,), "YY": (ncorr - 1,),                     # reference :182 (YY = -1)
-              "diagonals": (0, 3), "offdiagonals": (1, 2)}                                 # reference :222-229
+    planes = leaf_planes(zarr_path, ncorr)
     out_dev = torch.zeros(tuple(int(x) for x in shape), dtype=torch.complex64, device=dev)
     batch_size = max(1, int(batch_size))
     for start in range(0, len(tasks), batch_size):
@@ -143,6 +167,9 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         for t in batch:
             if t[4] not in planes:
                 raise ValueError(f"unknown leaf name {t[4]}")
+            if any(p < 0 or p >= ncorr for p in planes[t[4]]):
+                # the reference's numpy assignment raises IndexError here (decompress_ms.py:222-229 on a 2-correlation column)
+                raise ValueError(f"leaf {t[4]} maps to correlation plane(s) {planes[t[4]]} but the column has {ncorr}")
             stack = len(planes[t[4]])
             if t[0].shape[0] != stack * t[3].size:
                 raise ValueError(f"leaf {t[4]} has {t[0].shape[0]} rows, the table has {t[3].size} for this baseline")
@@ -171,6 +198,10 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         packed = torch.from_numpy(read_array(os.path.join(zarr_path, "FLAGS_ROW", "FLAGS_ROW")).astype(np.uint8)).to(dev)
         flag_row = eng.unpackbits(packed, out.shape[0]).cpu().numpy().astype(bool)
     corr_types = [9, 10, 11, 12][:ncorr] if ncorr <= 4 else list(range(ncorr))
+    if os.path.isdir(os.path.join(zarr_path, "POLARIZATION", "CORR_TYPE")):
+        ct = [int(x) for x in np.asarray(read_array(os.path.join(zarr_path, "POLARIZATION", "CORR_TYPE"))).reshape(-1)]
+        if len(ct) >= ncorr:
+            corr_types = ct[:ncorr]
     # WEIGHT_SPECTRUM / SIGMA_SPECTRUM: the reference multiplies U by diag(S) ONLY (decompress_ms.py:252-254: no WT),
     # expands a trailing axis and tiles it over the correlations, i.e. the columns come back as (row, 1, corr) with the
     # row profile of the weights and no channel dependence; both columns get the same array (:257-270). Kept as is.

@@ -166,12 +166,23 @@ class Engine:
         assert corr_sel.shape[0] == nbl and row_idx.is_contiguous() and corr_sel.is_contiguous()
         if out is None:
             out = torch.zeros((nbl * ncs // stack, stack * m, nchan), dtype=torch.complex64, device=data.device)
+        self._check_layout(row_idx, corr_sel, nrow, ncorr)
         with self._lock:
             self._bind_stream()
             rc = self.lib.vk_gather_baselines(self.h, self._ptr(data), nchan, ncorr, self._ptr(row_idx), nbl, m,
                                               self._ptr(corr_sel), ncs, stack, self._ptr(out))
         self._check(rc, "vk_gather_baselines")
         return out
+
+    def _check_layout(self, row_idx, corr_sel, nrow, ncorr):
+        """ValueError when a row index is outside [-1, nrow) or a correlation plane outside [0, ncorr): the reference's
+        numpy indexing raises IndexError there (decompress_ms.py:216-232); the kernels would touch foreign memory."""
+        bad = C.c_int32(0)
+        with self._lock:
+            self._bind_stream()
+            rc = self.lib.vk_check_layout_indices(self.h, self._ptr(row_idx), row_idx.numel(), int(nrow),
+                                                  self._ptr(corr_sel), corr_sel.numel(), int(ncorr), C.byref(bad))
+        self._check(rc, "vk_check_layout_indices")
 
     def scatter_baselines(self, cube, data, row_idx, corr_sel, stack=1):
         """Inverse of gather_baselines: writes the matrices of `cube` into data[row, chan, corr] in place
@@ -182,6 +193,7 @@ class Engine:
         ncs = corr_sel.shape[1]
         assert corr_sel.shape[0] == nbl and row_idx.is_contiguous() and corr_sel.is_contiguous()
         assert cube.is_contiguous() and data.is_contiguous() and cube.shape == (nbl * ncs // stack, stack * m, nchan)
+        self._check_layout(row_idx, corr_sel, nrow, ncorr)
         with self._lock:
             self._bind_stream()
             rc = self.lib.vk_scatter_baselines(self.h, self._ptr(cube), nchan, ncorr, self._ptr(row_idx), nbl, m,
