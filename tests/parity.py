@@ -79,7 +79,12 @@ def check_factors(a, U, S, Vt, k, decorrelation=None, compressionrank=None, labe
     # float32 round-off of r accumulated plane rotations / reflectors grows like sqrt(r): the floor is stated at r = 256
     roundoff = e_ref < ROUNDOFF_ERR * na
     floor = ERR_FLOOR * max(1.0, np.sqrt(min(a.shape) / 256.0)) if roundoff else 0.0
-    _record(label, sigma_over_1e4=float((ds / np.maximum(s_ref_full[:kk].astype(np.float64), 1e-30)).max() / S_RTOL) if kk else 0.0,
+    # raw sigma ratio: relative where a float32 singular value means something (>= 1e-4 sigma_1: below that the complex64
+    # input's own quantisation, 6e-8 sigma_1, already exceeds 1e-4 relative), absolute against sigma_1 for the rest
+    sref64 = s_ref_full[:kk].astype(np.float64)
+    big = sref64 >= 1e-4 * s1
+    _record(label, sigma_over_1e4=float((ds[big] / sref64[big]).max() / S_RTOL) if big.any() else 0.0,
+            sigma_tiny_abs_over_sigma1=float(ds[~big].max() / max(s1, 1e-30)) if (~big).any() else 0.0,
             **({"err_abs_over_normA_roundoff_cases": abs(e - e_ref) / max(na, 1e-30)} if roundoff else
                {"err_over_1e5": abs(e - e_ref) / max(e_ref, 1e-30) / ERR_RTOL}),
             rank_mismatch=float(k != k_ref))

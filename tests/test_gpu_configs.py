@@ -81,8 +81,8 @@ def test_c4_small_matrix_batch(eng, torch, kw):
 
 # ------------------------------------------------------------------------------------------------ C5
 def _random_factors(rng, B, m, n, k):
-    U = (rng.standard_normal((B, m, k)) + 1j * rng.standard_normal((B, m, k))).astype(np.complex64) / np.sqrt(2 * m)
-    Vt = (rng.standard_normal((B, k, n)) + 1j * rng.standard_normal((B, k, n))).astype(np.complex64) / np.sqrt(2 * n)
+    U = ((rng.standard_normal((B, m, k)) + 1j * rng.standard_normal((B, m, k))) / np.sqrt(2 * m)).astype(np.complex64)
+    Vt = ((rng.standard_normal((B, k, n)) + 1j * rng.standard_normal((B, k, n))) / np.sqrt(2 * n)).astype(np.complex64)
     S = (100.0 * np.exp(-0.25 * np.arange(k))[None, :] * (1 + 0.1 * rng.random((B, k)))).astype(np.float32)
     return U, S, Vt
 
@@ -172,3 +172,31 @@ def test_two_correlation_store_round_trip(eng, torch, tmp_path):
         assert back.data.shape == data.shape and back.corr_types == [9, 12]
         err = np.linalg.norm(back.data - data) / np.linalg.norm(data)
         assert err < 5e-3, (opt, err)
+
+
+# ------------------------------------------------------------------------------------------------ eigenvector paths
+@pytest.mark.parametrize("shape,dec", [((256, 1024), 0.98), ((128, 512), None), ((512, 2048), 0.99)])
+def test_full_spectrum_paths_agree(eng, torch, shape, dec):
+    """The twisted-factorisation + Newton-Schulz + GEMM eigenvector path ("eigvec_impl" = 0, default) against the implicit
+    QL path ("eigvec_impl" = 1) on the same cube: same ranks, singular values to 2e-5, both within the parity bounds."""
+    m, n = shape
+    A = _device_cube(eng, torch, 2, 4, m, n, nbl_total=64, bl_offset=20)
+    res = {}
+    for impl in (1, 0):
+        eng.set_option("eigvec_impl", impl)
+        try:
+            U, S, Vt, ranks, stats = eng.compress(A, decorrelation=dec)
+            torch.cuda.synchronize()
+            res[impl] = tuple(x.cpu().numpy() for x in (U, S, Vt, ranks, stats))
+        finally:
+            eng.set_option("eigvec_impl", 0)
+    assert np.all(res[0][4][:, 3] == 1) and np.all(res[1][4][:, 3] == 1)
+    Ah = A.cpu().numpy()
+    for b in range(A.shape[0]):
+        k0, k1 = int(res[0][3][b]), int(res[1][3][b])
+        assert abs(k0 - k1) <= 1, (b, k0, k1)
+        kk = min(k0, k1)
+        np.testing.assert_allclose(res[0][1][b, :kk], res[1][1][b, :kk], rtol=2e-5, atol=2e-6 * res[1][1][b, 0])
+        if b in (0, 1, 5):
+            parity.check_factors(Ah[b], res[0][0][b, :, :k0], res[0][1][b, :k0], res[0][2][b, :k0], k0, decorrelation=dec,
+                                 label=f"eigvec {shape} dec{dec} b={b}")

@@ -474,13 +474,15 @@ def test_direct_solver_hands_unconverged_passes_to_jacobi(eng, torch):
     """The QL iteration is limited per eigenvalue like LAPACK's; a matrix that hits the limit sends its pass back
     through the cyclic Jacobi solver. Forced here with a limit of one iteration."""
     A = _device_cube(eng, torch, 2, 4, 160, 320)
-    base = eng.compress(A)                            # full rank: every matrix takes the QL iteration
-    assert float(base[4][:, 2].min()) > 100          # QL iterations: the direct solver ran
     try:
+        eng.set_option("eigvec_impl", 1)              # the QL route (the default full-spectrum route does not iterate)
+        base = eng.compress(A)                        # full rank: every matrix takes the QL iteration
+        assert float(base[4][:, 2].min()) > 100      # QL iterations: the direct solver ran
         eng.set_option("ql_maxit", 1)
         got = eng.compress(A)
     finally:
         eng.set_option("ql_maxit", 60)
+        eng.set_option("eigvec_impl", 0)
     torch.cuda.synchronize()
     assert float(got[4][:, 3].min()) == 1 and float(got[4][:, 2].max()) <= 30   # converged, in Jacobi sweeps
     assert torch.equal(got[3], base[3])

@@ -176,6 +176,46 @@ def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_opt
     return processed
 
 
+def write_store_tables(zarr_path, vis, column="DATA", outcolumn="COMPRESSED_DATA"):
+    """The MAIN / ANTENNA / POLARIZATION columns the decompressors need (the reference converts every MS table,
+    compress_ms.py:138-194; the full MS -> zarr conversion is out of scope here). ROWID is a coordinate of MAIN, as in
+    the dask-ms datasets the reference writes (decompress_ms.py:159 reads maintable.coords["ROWID"])."""
+    import os
+
+    from .zarr_leaf import write_group
+    write_group(os.path.join(zarr_path, "MAIN"),
+                {"ANTENNA1": (vis.antenna1, ("row",)), "ANTENNA2": (vis.antenna2, ("row",)), "ROWID": (vis.rowid, ("row",))},
+                attrs={"visco_b200": {"column": column, "outcolumn": outcolumn}}, coordinates="ROWID")
+    write_group(os.path.join(zarr_path, "ANTENNA"), {"NAME": (np.array(vis.antenna_names, dtype="U"), ("row",))})
+    write_group(os.path.join(zarr_path, "POLARIZATION"),
+                {"CORR_TYPE": (np.array([vis.corr_types], dtype=np.int32), ("row", "corr"))})
+
+
+def write_store_flags(zarr_path, flags_packed, flags_row_packed):
+    """Groups FLAGS and FLAGS_ROW holding np.packbits(FLAG) / np.packbits(FLAG_ROW) with a `row` coordinate (reference
+    write_a_group_to_zarr, compress_ms.py:706-720; FLAGS_ROW is the reference's spelling, :482)."""
+    import os
+
+    from .zarr_leaf import write_group
+    for group, p in (("FLAGS_ROW", flags_row_packed), ("FLAGS", flags_packed)):
+        p = np.ascontiguousarray(p, dtype=np.uint8)
+        write_group(os.path.join(zarr_path, group), {group: (p, ("row",)), "row": (np.arange(p.shape[0]), ("row",))})
+
+
+def finalize_store(zarr_path, vis, chunk_size_row=10000, compressor="zstd", level=4, column="DATA"):
+    """Root .zgroup + root .zmetadata with MAIN/ANTENNA/POLARIZATION/FLAGS/FLAGS_ROW and a chunk-less MAIN/DATA entry:
+    the reference's decompressor takes DATA.shape / .dtype / .chunks and coords["ROWID"] from there
+    (decompress_ms.py:151-161; the column's chunks are deleted after compression, compress_ms.py:934-939)."""
+    from .zarr_leaf import consolidate_root, get_compressor, virtual_column_meta
+    nrow, nchan, ncorr = vis.data.shape
+    rows = int(min(max(1, int(chunk_size_row or nrow)), max(nrow, 1)))
+    codec = get_compressor(compressor, level) if compressor else None
+    virtual = virtual_column_meta("MAIN", "DATA", (nrow, nchan, ncorr), "<c8", (rows, nchan, ncorr), codec)
+    if column and column != "DATA":
+        virtual.update(virtual_column_meta("MAIN", column, (nrow, nchan, ncorr), "<c8", (rows, nchan, ncorr), codec))
+    return consolidate_root(zarr_path, virtual)
+
+
 def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, chunk_size_row: int = 10000,
                      overwrite: bool = True, compressor: str = "zstd", level: int = 4, nworkers: int = 4,
                      nthreads: int = 2, memory_limit: str = "4GB", direct_to_workers: bool = True,
@@ -215,13 +255,7 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
     os.makedirs(zarr_path, exist_ok=True)
     # the few MAIN / ANTENNA / POLARIZATION columns the decompressor needs (the full MS -> zarr conversion is out of scope)
     nrow, nchan, ncorr = vis.data.shape
-    write_group(os.path.join(zarr_path, "MAIN"),
-                {"ANTENNA1": (vis.antenna1, ("row",)), "ANTENNA2": (vis.antenna2, ("row",)), "ROWID": (vis.rowid, ("row",))},
-                attrs={"visco_b200": {"data_shape": [nrow, nchan, ncorr], "data_dtype": "<c8", "column": column,
-                                      "outcolumn": outcolumn}})
-    write_group(os.path.join(zarr_path, "ANTENNA"), {"NAME": (np.array(vis.antenna_names, dtype="U"), ("row",))})
-    write_group(os.path.join(zarr_path, "POLARIZATION"),
-                {"CORR_TYPE": (np.array([vis.corr_types], dtype=np.int32), ("row", "corr"))})
+    write_store_tables(zarr_path, vis, column=column, outcolumn=outcolumn)
     import torch
     eng = get_engine()
     dev = f"cuda:{eng.device}"
@@ -230,9 +264,9 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
     flag = vis.flag if vis.flag is not None else np.zeros(vis.data.shape, bool)
     flag_row = vis.flag_row if vis.flag_row is not None else np.zeros(nrow, bool)
     flag_dev = torch.from_numpy(flag).to(dev)
-    for group, packed in (("FLAGS", eng.packbits(flag_dev)), ("FLAGS_ROW", eng.packbits(torch.from_numpy(flag_row).to(dev)))):
-        p = packed.cpu().numpy()
-        write_group(os.path.join(zarr_path, group), {group: (p, ("row",)), "row": (np.arange(p.shape[0]), ("row",))})
+    write_store_flags(zarr_path, eng.packbits(flag_dev).cpu().numpy(), eng.packbits(torch.from_numpy(flag_row).to(dev)).cpu().numpy())
+    # root consolidated metadata: what the reference's decompressor opens (decompress_ms.py:151-161, 240-246)
+    finalize_store(zarr_path, vis, chunk_size_row=chunk_size_row, compressor=compressor, level=level, column=column)
     # WEIGHT_SPECTRUM: first correlation plane, rank 1, at the leaf <store>/WEIGHT_SPECTRUM (reference :486-503)
     if vis.weight_spectrum is not None:
         from .zarr_leaf import write_svd_to_zarr

@@ -63,9 +63,9 @@ int auto_chunk(const vk_context* h, int B, int m, int n, bool qr) {
     const int L = m < n ? n : m;
     if (qr) {
         // the direct solver has a latency-bound stage (the scalar QL iteration, one lane per matrix) whose duration
-        // does not depend on the number of matrices: take as many per pass as 8 GB of scratch allow
+        // does not depend on the number of matrices: take as many per pass as 14 GB of scratch allow
         const size_t per = vk_eigqr_scratch_bytes(1, r) + (size_t)r * r * 8;
-        size_t c = ((size_t)8 << 30) / per;
+        size_t c = ((size_t)14 << 30) / per;
         if (c < 1) c = 1;
         if (c > (size_t)B) c = B;
         return (int)c;
@@ -406,6 +406,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_generic = (int)v;
     else if (k == "eig_impl")
         h->eig_impl = (int)v;
+    else if (k == "eigvec_impl")
+        h->eigvec_impl = (int)v;
     else if (k == "ql_maxit")
         h->ql_maxit = (int)v;
     else if (k == "illcond_thr")

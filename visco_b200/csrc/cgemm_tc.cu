@@ -43,7 +43,7 @@ constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int CHUNK_KB = 4;
 
-enum { MODE_FORMV = 0, MODE_RECON = 1 };
+enum { MODE_FORMV = 0, MODE_RECON = 1, MODE_PLAIN = 2 };
 
 // (r0, i0, r1, i1) -> (-i0, r0, -i1, r1) : the row that multiplies the imaginary part of the A operand
 __device__ __forceinline__ float4 rot90(float4 v) { return make_float4(-v.y, v.x, -v.w, v.z); }
@@ -76,6 +76,7 @@ struct GemmArgs {
     const int32_t* ranks;  // [B]
     const float* S;        // MODE_RECON: [B][kmax] scale of contraction row c
     float* norm2;          // MODE_FORMV: [B][kmax] accumulates sum_v |D[c][v]|^2
+    const float* rowscale; // MODE_PLAIN (optional): [B][Mtot], D[i][:] = rowscale[i] * conj(P Q)[i][:]
     int Mtot;              // rows of D that must be written (kmax for FORMV, m for RECON)
     int Ntot;              // complex columns (n)
     int Ktot;              // complex contraction length available (m for FORMV, kmax for RECON)
@@ -99,10 +100,10 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int tile = blockIdx.x - b * tiles;
     const int m0 = (tile / g.tiles_n) * TILE_M;
     const int n0c = (tile % g.tiles_n) * TILE_NC;  // first complex column
-    const int rank = min(g.ranks ? g.ranks[b] : g.kmax, g.kmax);
+    const int rank = MODE == MODE_PLAIN ? 0 : min(g.ranks ? g.ranks[b] : g.kmax, g.kmax);
     // valid extents for this matrix
     const int Mvalid = MODE == MODE_FORMV ? rank : g.Mtot;
-    const int Kvalid = MODE == MODE_FORMV ? g.Ktot : rank;
+    const int Kvalid = MODE == MODE_RECON ? rank : g.Ktot;
     const int KB = (m0 < Mvalid) ? (Kvalid + KB_C - 1) / KB_C : 0;  // nothing to multiply for all-padding tiles
     const int NC = (KB + CHUNK_KB - 1) / CHUNK_KB;
 
@@ -257,11 +258,17 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const bool valid_row = gi < Mvalid;
             float2* drow = g.D + ((size_t)b * g.Mtot + gi) * g.Ntot;
             float nsum = 0.f;
+            float rs = 1.f, rsi = 1.f;
+            if (MODE == MODE_PLAIN && g.rowscale) {
+                rs = g.rowscale[(size_t)b * g.Mtot + gi];
+                rsi = -rs;
+            }
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
                 const int v = n0c + chalf * 64 + j;
                 float4 o = valid_row ? make_float4(acc[2 * j], acc[2 * j + 1], acc[2 * j + 2], acc[2 * j + 3])
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == MODE_PLAIN) o = make_float4(rs * o.x, rsi * o.y, rs * o.z, rsi * o.w);
                 if (v + 1 < g.Ntot) {
                     *reinterpret_cast<float4*>(drow + v) = o;
                     nsum += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
@@ -333,6 +340,7 @@ int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const in
         g.ranks = ranks + b0;
         g.S = nullptr;
         g.norm2 = norm2 + (size_t)b0 * kmax;
+        g.rowscale = nullptr;
         g.Mtot = kmax;
         g.Ntot = n;
         g.Ktot = m;
@@ -340,6 +348,38 @@ int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const in
         g.tiles_m = (kmax + TILE_M - 1) / TILE_M;
         g.tiles_n = (n + TILE_NC - 1) / TILE_NC;
         cgemm_tc_kernel<MODE_FORMV><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        VK_LAUNCH_CHECK(h);
+    }
+    return VK_OK;
+}
+
+// Plain batched product D[b] = P[b] Q[b] (P [B][M][K] K-major, Q [B][K][N], D [B][M][N], all complex64, contiguous), or
+// with rowscale != NULL: D[b][i][:] = rowscale[b][i] * conj((P Q)[i][:]). Needs K even and N a multiple of 16.
+// Used by the eigenvector stage (tridiag.cu): Newton-Schulz step and back-transformation of the eigenvectors of T.
+int vk_launch_cgemm_tc_plain(vk_context* h, const float2* P, const float2* Q, float2* D, const float* rowscale, int B,
+                             int M, int N, int K) {
+    if ((K % 2) || (N % 16)) return vk_fail(h, VK_EINVAL, "cgemm_tc_plain: needs even K and N % 16 == 0");
+    VK_CUDA(h, cudaFuncSetAttribute(cgemm_tc_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int maxB = 16384;
+    for (int b0 = 0; b0 < B; b0 += maxB) {
+        const int nb = (B - b0) < maxB ? (B - b0) : maxB;
+        CUtensorMap ma, mb;
+        int rc;
+        if ((rc = make_map_a(h, &ma, P + (size_t)b0 * M * K, M, K, nb))) return rc;
+        if ((rc = make_map_b(h, &mb, Q + (size_t)b0 * K * N, K, N, nb))) return rc;
+        GemmArgs g;
+        g.D = D + (size_t)b0 * M * N;
+        g.ranks = nullptr;
+        g.S = nullptr;
+        g.norm2 = nullptr;
+        g.rowscale = rowscale ? rowscale + (size_t)b0 * M : nullptr;
+        g.Mtot = M;
+        g.Ntot = N;
+        g.Ktot = K;
+        g.kmax = K;
+        g.tiles_m = (M + TILE_M - 1) / TILE_M;
+        g.tiles_n = (N + TILE_NC - 1) / TILE_NC;
+        cgemm_tc_kernel<MODE_PLAIN><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
         VK_LAUNCH_CHECK(h);
     }
     return VK_OK;
@@ -361,6 +401,7 @@ int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const flo
         g.ranks = ranks ? ranks + b0 : nullptr;
         g.S = S + (size_t)b0 * kmax;
         g.norm2 = nullptr;
+        g.rowscale = nullptr;
         g.Mtot = m;
         g.Ntot = n;
         g.Ktot = kmax;

@@ -45,6 +45,7 @@ struct vk_context {
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
+    int eigvec_impl = 0;     // eigenvectors of T on the full path: 0 = twisted factorisation + Newton-Schulz + GEMMs, 1 = implicit QL
     int ql_maxit = 60;       // QL iterations allowed per eigenvalue (tests lower it to exercise the Jacobi fallback)
     int64_t eig_fallbacks = 0;  // internal passes the direct solver handed back to the Jacobi solver
     // retained sigma_k / sigma_1 below this: redo the matrix without a Gram product (0 = never). Measured error of
@@ -159,6 +160,8 @@ int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const in
                        int B, int m, int n, int kmax);
 int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, float2* out,
                        int B, int m, int n, int kmax);
+int vk_launch_cgemm_tc_plain(vk_context* h, const float2* P, const float2* Q, float2* D, const float* rowscale, int B,
+                             int M, int N, int K);
 int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
                           int m, int n, int kmax, float2* out);
 int vk_launch_synth(vk_context* h, float2* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,

@@ -1256,10 +1256,191 @@ __global__ void __launch_bounds__(FQ_THREADS, (EPL * RPW <= 32) ? 2 : 1)
     }
 }
 
+
+// =====================================================================================================================
+// Full spectrum without the QL iteration ("eigvec_impl" = 0, r a multiple of 16, r >= 128): after the tridiagonalisation
+//   (a) every eigenvalue of T by Sturm bisection (one thread per eigenvalue),
+//   (b) one twisted factorisation per eigenvalue for its eigenvector of T (one thread per eigenvector, no
+//       reorthogonalisation): Zt[t][:] = z_t, stored as complex numbers with zero imaginary part,
+//   (c) E = Zt Zt^T - I on the tensor cores (gram_tc.cu); max |E| per matrix decides: below EV_ORTHO_LIMIT one
+//       Newton-Schulz step Zt <- (I - E/2) Zt (tcgen05 GEMM) restores orthonormality to ~1e-6, above it (numerically
+//       multiple eigenvalues: exactly rank-deficient input, repeated singular values) the matrix is left to the QL path,
+//   (d) Xt = Zt (Q D)^T as one tcgen05 GEMM against the accumulated reflectors, written as lambda_t conj(Xt[t][:]).
+// Measured in float32 (tools/proto_mrrr.py) on signal + noise and noise-only Gram matrices of r = 256 / 512: max |E| =
+// 6e-5 .. 3e-4 before and 6e-7 .. 1e-6 after the Newton-Schulz step; residual |T z - lambda z| <= 6e-7 |T|. Close
+// eigenvalues only mix their own vectors, which changes neither a retained subspace nor (to second order) the singular
+// values that the factor stage refines from the matrix itself. Replaces the serial QL chase (tql_kernel) and the
+// barrier-bound rotation application (rotapply_kernel) by work that is either embarrassingly parallel or a GEMM.
+constexpr float EV_ORTHO_LIMIT = 0.05f;
+constexpr int EV_THREADS = 128;
+
+__global__ void __launch_bounds__(EV_THREADS) bisect_full_kernel(int r, const float* __restrict__ dall,
+                                                                 const float* __restrict__ eall,
+                                                                 float* __restrict__ lamall) {
+    extern __shared__ float bs_sm[];
+    float* d = bs_sm;
+    float* e2 = bs_sm + r;
+    __shared__ float s_lo[EV_THREADS / 32], s_hi[EV_THREADS / 32];
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    float lo = 3.4e38f, hi = -3.4e38f;
+    for (int i = tid; i < r; i += EV_THREADS) {
+        const float di = dall[(size_t)b * r + i];
+        const float ei = i < r - 1 ? eall[(size_t)b * r + i] : 0.f;
+        const float ep = i > 0 ? eall[(size_t)b * r + i - 1] : 0.f;
+        d[i] = di;
+        e2[i] = ei * ei;
+        const float rad = fabsf(ei) + fabsf(ep);
+        lo = fminf(lo, di - rad);
+        hi = fmaxf(hi, di + rad);
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    if (lane == 0) s_lo[tid >> 5] = lo, s_hi[tid >> 5] = hi;
+    __syncthreads();
+    for (int w = 0; w < EV_THREADS / 32; ++w) lo = fminf(lo, s_lo[w]), hi = fmaxf(hi, s_hi[w]);
+    const float scale = fmaxf(fabsf(lo), fabsf(hi));
+    const float pivmin = fmaxf(1e-30f, 1e-14f * scale * scale);
+    const int t = blockIdx.x * EV_THREADS + tid;  // t-th largest eigenvalue
+    if (t >= r) return;
+    const int idx = r - 1 - t;
+    float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+    for (int it = 0; it < 48; ++it) {
+        const float mid = 0.5f * (a + c);
+        if (!(mid > a && mid < c)) break;
+        if (sturm_count(d, e2, r, mid, pivmin) > idx) c = mid;
+        else a = mid;
+    }
+    lamall[(size_t)b * r + t] = 0.5f * (a + c);
+}
+
+// One thread per eigenvector. The pivots of both factorisations live in global scratch laid out [i][t] (coalesced over
+// the eigenvalue index t); the finished vector is transposed through shared memory so that Zt[t][:] is written in
+// 128-byte rows. flag[b] is cleared when a vector overflows.
+__global__ void __launch_bounds__(EV_THREADS) twisted_full_kernel(int r, const float* __restrict__ dall,
+                                                                  const float* __restrict__ eall,
+                                                                  const float* __restrict__ lamall,
+                                                                  float* __restrict__ dpall, float* __restrict__ dmall,
+                                                                  float2* __restrict__ Ztall, int32_t* __restrict__ flag) {
+    extern __shared__ float tw_sm[];
+    float* d = tw_sm;
+    float* e = tw_sm + r;
+    float* tile = tw_sm + 2 * r;  // [EV_THREADS / 32][32][33]
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < r; i += EV_THREADS) {
+        d[i] = dall[(size_t)b * r + i];
+        e[i] = i < r - 1 ? eall[(size_t)b * r + i] : 0.f;
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * EV_THREADS;
+    const int t = t0 + tid;
+    const bool live = t < r;
+    float* dp = dpall + (size_t)b * r * r + t;  // element i at dp[i * r]
+    float* dm = dmall + (size_t)b * r * r + t;
+    float sc = 0.f;
+    int bad = 0;
+    if (live) {
+        const float lam = lamall[(size_t)b * r + t];
+        const float pivmin = fmaxf(1e-30f, 1e-14f * lam * lam);
+        float q = d[r - 1] - lam;
+        if (fabsf(q) < pivmin) q = -pivmin;
+        dm[(size_t)(r - 1) * r] = q;
+        for (int i = r - 2; i >= 0; --i) {
+            const float ei = e[i];
+            q = d[i] - lam - ei * ei / q;
+            if (fabsf(q) < pivmin) q = -pivmin;
+            dm[(size_t)i * r] = q;
+        }
+        float p = d[0] - lam;
+        if (fabsf(p) < pivmin) p = -pivmin;
+        dp[0] = p;
+        float best = fabsf(q);  // gamma_0 = dm[0]
+        int kt = 0;
+        for (int i = 1; i < r; ++i) {
+            const float ei = e[i - 1];
+            p = d[i] - lam - ei * ei / p;
+            if (fabsf(p) < pivmin) p = -pivmin;
+            dp[(size_t)i * r] = p;
+            const float gam = fabsf(p + dm[(size_t)i * r] - (d[i] - lam));
+            if (gam < best) best = gam, kt = i;
+        }
+        // z[kt] = 1; upward with the forward pivots, downward with the backward ones (z overwrites dp)
+        float nrm = 1.f, zi = 1.f;
+        for (int i = kt - 1; i >= 0; --i) {
+            zi = -(e[i] / dp[(size_t)i * r]) * zi;
+            dp[(size_t)i * r] = zi;
+            nrm = fmaf(zi, zi, nrm);
+        }
+        zi = 1.f;
+        for (int i = kt + 1; i < r; ++i) {
+            zi = -(e[i - 1] / dm[(size_t)i * r]) * zi;
+            dp[(size_t)i * r] = zi;
+            nrm = fmaf(zi, zi, nrm);
+        }
+        dp[(size_t)kt * r] = 1.f;
+        sc = rsqrtf(nrm);
+        if (!(nrm < 3e38f)) bad = 1, sc = 0.f;
+    }
+    if (bad) flag[b] = 0;
+    // transpose: this warp's 32 vectors, 32 entries at a time
+    float* tl = tile + warp * 32 * 33;
+    float2* Zt = Ztall + (size_t)b * r * r;
+    const int tw0 = t0 + warp * 32;
+    for (int i0 = 0; i0 < r; i0 += 32) {
+        __syncwarp();
+#pragma unroll 4
+        for (int ii = 0; ii < 32; ++ii) {
+            const int i = i0 + ii;
+            tl[ii * 33 + lane] = (live && i < r) ? dp[(size_t)i * r] * sc : 0.f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int tt = 0; tt < 32; ++tt) {
+            const int i = i0 + lane;
+            if (tw0 + tt < r && i < r) Zt[(size_t)(tw0 + tt) * r + i] = make_float2(tl[lane * 33 + tt], 0.f);
+        }
+    }
+}
+
+// W holds Zt Zt^T (real part; from gram_tc). In place: P = 1.5 I - 0.5 Re W (imaginary part zero), the left factor of the
+// Newton-Schulz step. flag[b] &= (max |Re W - I| <= EV_ORTHO_LIMIT); done / sweeps are preset for the matrices that stay.
+__global__ void __launch_bounds__(256) nsprep_kernel(float2* __restrict__ Wall, int r, int32_t* __restrict__ flag,
+                                                     unsigned* __restrict__ emax) {
+    const int b = blockIdx.y;
+    float2* W = Wall + (size_t)b * r * r;
+    float mx = 0.f;
+    const size_t n = (size_t)r * r;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / r), j = (int)(idx - (size_t)i * r);
+        const float g = W[idx].x;
+        const float ee = g - (i == j ? 1.f : 0.f);
+        const float ae = fabsf(ee);
+        mx = (ae > mx || !(ae == ae)) ? (ae == ae ? ae : 3e38f) : mx;
+        W[idx] = make_float2((i == j ? 1.f : 0.f) - 0.5f * ee, 0.f);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(emax + b, __float_as_uint(mx));  // non-negative floats order like unsigned
+}
+__global__ void __launch_bounds__(128) nsflag_kernel(const unsigned* __restrict__ emax, int B, int32_t* __restrict__ flag,
+                                                     int32_t* __restrict__ done, int32_t* __restrict__ sweeps) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float mx = __uint_as_float(emax[b]);
+    const int ok = (flag[b] != 0 && mx <= EV_ORTHO_LIMIT) ? 1 : 0;
+    flag[b] = ok;
+    if (ok) {
+        done[b] = 1;
+        sweeps[b] = 0;
+    }
+}
+__global__ void __launch_bounds__(128) fill_i32_kernel(int32_t* __restrict__ p, int n, int32_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct EigScratch {
-    size_t X, d, e, tau, ph, lam, cs, sw, meta, lamtop, flag, kvec, z, dm, total;
+    size_t X, d, e, tau, ph, lam, cs, sw, meta, lamtop, flag, kvec, z, dm, zt, zt2, emax, total;
     int cap, scap, lcap;
 };
 
@@ -1283,6 +1464,11 @@ EigScratch eig_layout(int B, int r) {
     s.kvec = off, off += al((size_t)B * 4);
     s.z = off, off += al((size_t)B * TK_MAXK * r * 4);
     s.dm = off, off += al((size_t)B * TK_MAXK * r * 4);
+    // full-spectrum eigenvector path: Zt and its Newton-Schulz update (complex r x r each); the pivots of the twisted
+    // factorisations (2 r^2 floats) reuse the rotation store `cs` (1.5 r^2 + 256 float2), which only the QL path writes
+    s.zt = off, off += al((size_t)B * r * r * 8);
+    s.zt2 = off, off += al((size_t)B * r * r * 8);
+    s.emax = off, off += al((size_t)B * 4);
     s.total = off;
     return s;
 }
@@ -1457,6 +1643,72 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         else rc = launch_backtr<32, 2>(h, st, W, B, r, ld, wstride, 0, tau, ph, L, sc, done_dev, sweeps_dev, kvec, lamall);
         if (rc) return rc;
         skip = flag;
+    }
+    // full spectrum: eigenvectors of T by twisted factorisation + Newton-Schulz + GEMM back-transformation (see above);
+    // the QL kernels below then only see the matrices that path gave up (flag 0), normally none
+    const bool mrrr = skip == nullptr && h->eigvec_impl != 1 && r >= 128 && (r % 16) == 0 && ld == r;
+    if (mrrr) {
+        float* lam = reinterpret_cast<float*>(sc + L.lam);
+        int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
+        unsigned* emax = reinterpret_cast<unsigned*>(sc + L.emax);
+        float* dp = reinterpret_cast<float*>(sc + L.cs);
+        float* dm = dp + (size_t)B * r * r;
+        float2* Zt = reinterpret_cast<float2*>(sc + L.zt);
+        float2* Zt2 = reinterpret_cast<float2*>(sc + L.zt2);
+        fill_i32_kernel<<<(B + 127) / 128, 128, 0, st>>>(flag, B, 1);
+        VK_LAUNCH_CHECK(h);
+        VK_CUDA(h, cudaMemsetAsync(emax, 0, (size_t)B * 4, st));
+        const dim3 egrid((r + EV_THREADS - 1) / EV_THREADS, B);
+        bisect_full_kernel<<<egrid, EV_THREADS, (size_t)2 * r * 4, st>>>(r, d, e, lam);
+        VK_LAUNCH_CHECK(h);
+        twisted_full_kernel<<<egrid, EV_THREADS, ((size_t)2 * r + (EV_THREADS / 32) * 32 * 33) * 4, st>>>(r, d, e, lam, dp, dm,
+                                                                                                     Zt, flag);
+        VK_LAUNCH_CHECK(h);
+        if (dbg) cudaEventRecord(ev[2], st);
+        if (dbg) cudaEventRecord(ev[3], st);
+        // reflectors of every matrix -> X = (Q D)^T; W is free from here on
+        if (r <= 128) rc = launch_formq<4, 4>(h, st, W, B, r, ld, wstride, tau, ph, X, nullptr);
+        else if (r <= 256) rc = launch_formq<8, 4>(h, st, W, B, r, ld, wstride, tau, ph, X, nullptr);
+        else if (r <= 512) rc = launch_formq<16, 2>(h, st, W, B, r, ld, wstride, tau, ph, X, nullptr);
+        else rc = launch_formq<32, 1>(h, st, W, B, r, ld, wstride, tau, ph, X, nullptr);
+        if (rc) return rc;
+        if (dbg) cudaEventRecord(ev[4], st);
+        // W <- Zt Zt^H (= Zt Zt^T: zero imaginary parts), then P = I - E/2 in place and the verdict per matrix
+        if ((rc = vk_launch_gram_tc(h, Zt, B, r, r, W))) return rc;
+        {
+            int gx = (int)(((size_t)r * r + 255) / 256);
+            if (gx > 64) gx = 64;
+            nsprep_kernel<<<dim3(gx, B), 256, 0, st>>>(W, r, flag, emax);
+            VK_LAUNCH_CHECK(h);
+            nsflag_kernel<<<(B + 127) / 128, 128, 0, st>>>(emax, B, flag, done_dev, sweeps_dev);
+            VK_LAUNCH_CHECK(h);
+        }
+        // Zt2 = P Zt ; W[t][:] = lambda_t conj((Zt2 X)[t][:])
+        if ((rc = vk_launch_cgemm_tc_plain(h, W, Zt, Zt2, nullptr, B, r, r, r))) return rc;
+        if ((rc = vk_launch_cgemm_tc_plain(h, Zt2, X, W, lam, B, r, r, r))) return rc;
+        skip = flag;
+        // the matrices that were given up: QL on T, rotations applied to X (already formed), W rewritten
+        {
+            const size_t smem = (size_t)2 * (r + 2) * 4 + (size_t)RA_NS_MAX * 4;
+            VK_CUDA(h, cudaFuncSetAttribute(tql_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tql_kernel<<<B, 32, smem, st>>>(r, d, e, lam, reinterpret_cast<float2*>(sc + L.cs),
+                                            reinterpret_cast<SweepRec*>(sc + L.sw), reinterpret_cast<int32_t*>(sc + L.meta),
+                                            L.cap, L.scap, L.lcap, skip, h->ql_maxit > 0 ? h->ql_maxit : QL_MAXIT, nslots);
+            VK_LAUNCH_CHECK(h);
+        }
+        rc = nslots == 64 ? launch_rotapply<64>(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip)
+                          : launch_rotapply<128>(h, st, X, B, r, L, sc, W, ld, wstride, done_dev, sweeps_dev, skip);
+        if (dbg) {
+            cudaEventRecord(ev[5], st);
+            cudaEventSynchronize(ev[5]);
+            float t[5];
+            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+            for (int i = 0; i < 5; ++i) h->eig_ms[i] += t[i];
+            if (h->stage_timing >= 2)
+                fprintf(stderr, "[eigqr B=%d r=%d full] tridiag %.3f  bisect+twisted %.3f  formq %.3f  gram+NS+back %.3f ms\n", B, r,
+                        t[0], t[1], t[3], t[4]);
+        }
+        return rc;
     }
     if (dbg) cudaEventRecord(ev[2], st);
     // the scalar QL iteration is latency bound (one lane per matrix): it runs alone - sharing the SMs with another

@@ -135,7 +135,7 @@ def _zarray_meta(a: np.ndarray, codec) -> dict:
             "zarr_format": 2}
 
 
-def write_array(group_dir: Path, name: str, a: np.ndarray, dims, codec=None) -> dict:
+def write_array(group_dir: Path, name: str, a: np.ndarray, dims, codec=None, extra_attrs: dict | None = None) -> dict:
     """Write one zarr-v2 array as a single chunk; returns {relative key: json} for the consolidated metadata."""
     a = np.ascontiguousarray(a)
     if a.dtype.byteorder == ">":
@@ -143,7 +143,7 @@ def write_array(group_dir: Path, name: str, a: np.ndarray, dims, codec=None) -> 
     d = Path(group_dir) / name
     d.mkdir(parents=True, exist_ok=True)
     meta = _zarray_meta(a, codec)
-    attrs = {"_ARRAY_DIMENSIONS": list(dims)}
+    attrs = {"_ARRAY_DIMENSIONS": list(dims), **(extra_attrs or {})}
     (d / ".zarray").write_text(json.dumps(meta, indent=4, sort_keys=True))
     (d / ".zattrs").write_text(json.dumps(attrs, indent=4))
     if a.size:
@@ -152,17 +152,56 @@ def write_array(group_dir: Path, name: str, a: np.ndarray, dims, codec=None) -> 
     return {f"{name}/.zarray": meta, f"{name}/.zattrs": attrs}
 
 
-def write_group(group_dir: Path, arrays: dict, attrs: dict | None = None, codec_for=None):
-    """arrays: name -> (ndarray, dims). Writes .zgroup/.zattrs/.zmetadata and every array."""
+def write_group(group_dir: Path, arrays: dict, attrs: dict | None = None, codec_for=None, coordinates: str | None = None):
+    """arrays: name -> (ndarray, dims). Writes .zgroup/.zattrs/.zmetadata and every array. `coordinates` names a
+    non-dimension coordinate array of the group (e.g. "ROWID"): it is recorded CF-style in the ``coordinates`` attribute
+    of every other array that shares its dimension, which is how xarray marks it as a coordinate on read."""
     group_dir = Path(group_dir)
     group_dir.mkdir(parents=True, exist_ok=True)
     zgroup = {"zarr_format": 2}
     (group_dir / ".zgroup").write_text(json.dumps(zgroup, indent=4))
     (group_dir / ".zattrs").write_text(json.dumps(attrs or {}, indent=4))
     cons = {".zattrs": attrs or {}, ".zgroup": zgroup}
+    cdims = set(arrays[coordinates][1]) if coordinates and coordinates in arrays else set()
     for name, (a, dims) in arrays.items():
-        cons.update(write_array(group_dir, name, a, dims, codec_for(name) if codec_for else None))
+        extra = {"coordinates": coordinates} if (cdims and name != coordinates and cdims <= set(dims)) else None
+        cons.update(write_array(group_dir, name, a, dims, codec_for(name) if codec_for else None, extra))
     (group_dir / ".zmetadata").write_text(json.dumps({"metadata": cons, "zarr_consolidated_format": 1}, indent=4))
+
+
+def consolidate_root(zarr_path, virtual: dict | None = None):
+    """Root ``.zgroup`` + root ``.zmetadata`` of a compressed store: the consolidated view the reference's decompressor
+    opens (``xr.open_zarr(zarr_path, group="MAIN" | "ANTENNA" | "FLAGS" | "FLAGS_ROW", consolidated=True)``,
+    reference decompress_ms.py:151-152, 240, 245 - zarr resolves ``consolidated=True`` against the ``.zmetadata`` at the
+    ROOT of the store and never looks at per-group files). Keys are ``<group>/.zgroup``, ``<group>/.zattrs``,
+    ``<group>/<array>/.zarray``, ``<group>/<array>/.zattrs`` for every top-level group and the arrays directly inside
+    it (the per-baseline leaf trees below MAIN/<outcolumn> are separate stores with their own ``.zmetadata``, as in the
+    reference, and are not listed). ``virtual`` adds metadata-only entries: the reference deletes the chunks of the
+    raw visibility column but still reads ``maintable.DATA.shape / .dtype / .chunks`` from this file
+    (compress_ms.py:934-939 vs decompress_ms.py:157-161)."""
+    root = Path(zarr_path)
+    zgroup = {"zarr_format": 2}
+    (root / ".zgroup").write_text(json.dumps(zgroup, indent=4))
+    md = {".zgroup": zgroup}
+    for g in sorted(p for p in root.iterdir() if p.is_dir() and (p / ".zgroup").exists()):
+        md[f"{g.name}/.zgroup"] = json.loads((g / ".zgroup").read_text())
+        md[f"{g.name}/.zattrs"] = json.loads((g / ".zattrs").read_text()) if (g / ".zattrs").exists() else {}
+        for a in sorted(p for p in g.iterdir() if p.is_dir() and (p / ".zarray").exists()):
+            md[f"{g.name}/{a.name}/.zarray"] = json.loads((a / ".zarray").read_text())
+            md[f"{g.name}/{a.name}/.zattrs"] = json.loads((a / ".zattrs").read_text()) if (a / ".zattrs").exists() else {}
+    md.update(virtual or {})
+    (root / ".zmetadata").write_text(json.dumps({"metadata": md, "zarr_consolidated_format": 1}, indent=4))
+    return md
+
+
+def virtual_column_meta(group: str, name: str, shape, dtype: str, chunks, codec=None, dims=("row", "chan", "corr"),
+                        coordinates: str = "ROWID") -> dict:
+    """``.zarray`` / ``.zattrs`` entries of a column that has metadata but no chunks (see consolidate_root)."""
+    dt = np.dtype(dtype)
+    return {f"{group}/{name}/.zarray": {"chunks": [int(c) for c in chunks], "compressor": codec, "dtype": dt.str,
+                                         "fill_value": _fill_json(dt), "filters": None, "order": "C",
+                                         "shape": [int(x) for x in shape], "zarr_format": 2},
+            f"{group}/{name}/.zattrs": {"_ARRAY_DIMENSIONS": list(dims), "coordinates": coordinates}}
 
 
 def _read_vlen_utf8(array_dir: Path, meta: dict) -> np.ndarray:
