@@ -1,19 +1,32 @@
 #!/usr/bin/env python
 """bench.py — round trip (compress -> reconstruct) throughput of the VISCO hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload kat7|meerkat|small|ska] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload kat7|meerkat|small] [--impl ours|reference]
+                    [--extras 0|1]
 
-One "step" = one pass of the hot path over one batch of synthetic visibilities: vk_compress_batched
-(Gram on tcgen05 -> Jacobi eigensolver -> select/truncate -> factor formation) followed by vk_reconstruct_batched.
-Default workload = BASELINE.json configs[1] (KAT-7 shape: 28 baselines x 4 corr x 256 time x 1024 chan complex64,
-fixed rank k = 8), one such cube per GPU (weak scaling; no collective on the data path, one NCCL all-gather of the
-per-matrix ranks/statistics after the timed region).
+Workload (default): BASELINE.json configs[1], the configuration the metric is quoted on — synthetic KAT-7 shape, 28
+baselines x 4 corr x 256 time x 1024 chan complex64 (one "cube" = 112 matrices, 235 MB), fixed rank k = 8; one set of
+cubes per GPU (weak scaling, no collective on the data path; one NCCL all-gather of the per-matrix ranks and statistics
+after the timed region). One "step" = CUBES_PER_STEP such cubes, each a separate vk_compress_batched
+(tcgen05 Gram -> Householder tridiagonalisation -> eigenpairs -> select/truncate -> factor formation) followed by
+vk_reconstruct_batched, rotating over NCUBES distinct resident cubes, so that K steps last seconds, the clocks are the
+steady-state ones and every cube is read from HBM, not L2.
 
-Prints ONE JSON line (rank 0). `value` = visibilities compressed+reconstructed per second with the cube resident in
-HBM, CUDA-event timed, max over ranks. `e2e` = same metric through the host-buffer C ABI (vk_compress_host /
-vk_reconstruct_host) with pinned host inputs and outputs, copies inside the timed region.
-`--impl reference` times the reference's CPU path (oracle port of np.linalg.svd + svd_flip + energy rule +
-(U*S)@Vt, one process per host core, BLAS threads = 1) on the same workload.
+Prints ONE JSON line (rank 0):
+  value      visibilities compressed+reconstructed per second, cubes resident in HBM, CUDA events on the launching
+             stream, max over ranks
+  e2e        the same metric through the host-buffer C ABI (vk_compress_host + vk_reconstruct_host on pinned host
+             arrays, every copy inside the timed region), E2E_THREADS host threads each with its own handle and buffers
+             so that the upload of one cube, the factorisation of another and the download of a third overlap (PCIe is
+             full duplex); also the single-thread figure and the measured pinned-memcpy ceiling of this host
+  roofline   the dominant kernel by time with SURVEY 8(d)'s algorithmic bytes over the measured HBM peak;
+             roofline.stages = every stage against the roofline that bounds it (Gram: tensor, measured TF32 peak;
+             reconstruction / factor formation: HBM; eigen stage: modelled flops over the measured FP32 peak);
+             roofline.other_workloads = the other BASELINE configs measured in the same invocation (C3 shard, C4,
+             C5 reconstruction sweep k = 1..32 over the full 78 804-matrix cube, ring-buffered)
+  cpu_baseline  the oracle port of the reference's CPU path on the box's host cores, same inputs (D2H copies)
+`--impl reference` times the reference's CPU path alone (oracle port of np.linalg.svd + svd_flip + energy rule +
+(U*S)@Vt, one process per host core, BLAS threads = 1) on the same config, one bounded sample per step.
 """
 import argparse
 import json
@@ -32,9 +45,17 @@ WORKLOADS = {
     "meerkat": (260, 4, 512, 4096, dict(decorrelation=0.99),
                 "configs[2]: MeerKAT-64 shape, 260-baseline shard (1/8 of 2080) x 4 corr x 512 x 4096, decorrelation 0.99"),
     "small": (2080, 4, 64, 64, dict(compressionrank=8), "configs[3]: 2080 bl x 4 corr x 64 x 64, one-sided Jacobi path"),
-    "ska": (2048, 4, 128, 2048, dict(compressionrank=8), "configs[4]-like: 2048 bl x 4 corr x 128 x 2048, k=8"),
 }
+CUBES_PER_STEP = {"kat7": 32, "meerkat": 1, "small": 8}
+NCUBES = {"kat7": 4, "meerkat": 1, "small": 4}
+E2E_THREADS = 3
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
+
+
+def make_config(args):
+    """The SAME dict in both arms (the driver compares them)."""
+    nbl, ncorr, m, n, kw, desc = WORKLOADS[args.workload]
+    return {"workload": desc, "shape_per_gpu": [nbl * ncorr, m, n], "cubes_per_step": CUBES_PER_STEP[args.workload], **kw}
 
 
 def algorithmic_bytes(B, m, n, kbar):
@@ -43,7 +64,7 @@ def algorithmic_bytes(B, m, n, kbar):
 
 
 def peaks():
-    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             j = json.load(f)
@@ -53,6 +74,17 @@ def peaks():
     except Exception:
         pass
     return p
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch of a kernel from a committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    {key: {"bytes": ..., "source": file}}), or (None, None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            e = json.load(f).get(key)
+        return (float(e["bytes"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -98,6 +130,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (intersection with what the cgroup allows), so pinned
+    host buffers are first-touched on the GPU's NUMA node. Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return f"pinned to {len(use)} GPU-local cpus {use[0]}-{use[-1]}"
+        return f"no narrower GPU-local cpu set ({len(allowed)} allowed cpus, {len(local)} GPU-local)"
+    except Exception as e:  # pragma: no cover
+        return f"not bound ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------- CPU reference arm
 def _cpu_one(args):
     a, kw = args
@@ -108,27 +160,29 @@ def _cpu_one(args):
 
 def cpu_worker_main(path):
     """Child process: OPENBLAS/OMP threads were pinned to 1 in the environment BEFORE numpy was imported, and there is
-    no CUDA context here, so forking a pool is safe. Prints one JSON line {vis_per_s, seconds}."""
+    no CUDA context here, so forking a pool is safe. Prints one JSON line {vis_per_s, seconds, per_rep}."""
     import multiprocessing as mp
     import numpy as np
     with np.load(path, allow_pickle=True) as z:
-        cube, kw, procs, reps = z["cube"], z["kw"].item(), int(z["procs"]), int(z["reps"])
+        cube, kw, procs, reps, warm = z["cube"], z["kw"].item(), int(z["procs"]), int(z["reps"]), int(z["warm"])
     ctx = mp.get_context("fork")
     secs = []
     with ctx.Pool(procs) as pool:
-        pool.map(_cpu_one, [(cube[i], kw) for i in range(min(procs, len(cube)))])  # warm the workers
+        pool.map(_cpu_one, [(cube[i], kw) for i in range(min(procs, len(cube)))])  # start the workers
+        for _ in range(warm):
+            pool.map(_cpu_one, [(cube[i], kw) for i in range(len(cube))], chunksize=1)
         for _ in range(reps):
             t0 = time.perf_counter()
             pool.map(_cpu_one, [(cube[i], kw) for i in range(len(cube))], chunksize=1)
             secs.append(time.perf_counter() - t0)
-    print(json.dumps({"vis_per_s": cube[0].size * len(cube) * reps / sum(secs), "seconds": sum(secs)}), flush=True)
+    print(json.dumps({"vis_per_s": cube[0].size * len(cube) * reps / sum(secs), "seconds": sum(secs), "per_rep": secs}), flush=True)
     return 0
 
 
-def cpu_roundtrip_rate(cube, kw, procs, reps=1):
+def cpu_roundtrip_rate(cube, kw, procs, reps=1, warm=0):
     """oracle port on `procs` processes, BLAS threads = 1 each (mirrors the reference's -nw N -nt 1), run in a fresh
     interpreter so that neither this process's CUDA context nor its BLAS thread pool is forked.
-    Returns (visibilities per second, seconds)."""
+    Returns (visibilities per second, seconds, per-repetition seconds)."""
     import subprocess
     import tempfile
     import numpy as np
@@ -137,39 +191,41 @@ def cpu_roundtrip_rate(cube, kw, procs, reps=1):
         env.pop(k, None)
     with tempfile.TemporaryDirectory() as d:
         path = os.path.join(d, "sample.npz")
-        np.savez(path, cube=cube, kw=np.array(kw, dtype=object), procs=procs, reps=reps)
+        np.savez(path, cube=cube, kw=np.array(kw, dtype=object), procs=procs, reps=reps, warm=warm)
         outp = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", path], env=env, check=True,
-                              capture_output=True, text=True, timeout=1200).stdout
+                              capture_output=True, text=True, timeout=3000).stdout
     j = json.loads(outp.strip().splitlines()[-1])
-    return j["vis_per_s"], j["seconds"]
+    return j["vis_per_s"], j["seconds"], j["per_rep"]
+
+
+def cpu_sample_size(B, m, n, procs, seconds=15.0):
+    """matrices that keep `procs` single-threaded workers busy for about `seconds`"""
+    per_matrix_s = 2.5e-9 * m * n * min(m, n)           # ~0.17 s at 256 x 1024 (survey probe)
+    return max(1, min(B, procs * max(1, int(seconds / max(per_matrix_s, 1e-6)))))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import numpy as np
     from oracle.synth_np import synth_cube
     nbl, ncorr, m, n, kw, desc = WORKLOADS[args.workload]
     procs = len(os.sched_getaffinity(0))
-    # bounded sample of the workload: ~10-30 s of CPU work per step
-    per_matrix_s = 2.5e-9 * m * n * min(m, n)           # ~0.17 s at 256 x 1024 (survey probe)
-    nsample = int(max(min(nbl * ncorr, 20.0 / max(per_matrix_s, 1e-6)), min(nbl * ncorr, procs)))
+    # one bounded sample of the workload per step: about one second of work on all host cores
+    nsample = cpu_sample_size(nbl * ncorr, m, n, procs, seconds=1.5)
     nsample = max(ncorr, nsample // ncorr * ncorr)
     cube = synth_cube(nsample // ncorr, ncorr, m, n, nbl_total=nbl * args.gpus)
-    if args.warmup:
-        cpu_roundtrip_rate(cube[:max(1, min(len(cube), procs))], kw, procs, reps=args.warmup)
-    rate, _ = cpu_roundtrip_rate(cube, kw, procs, reps=args.steps)
+    rate, secs, per_rep = cpu_roundtrip_rate(cube, kw, procs, reps=args.steps, warm=args.warmup)
     value = rate / 1e9
-    full_vis = nbl * ncorr * m * n * args.gpus
     line = {
         "metric": METRIC, "value": value, "unit": "GVis/s", "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * full_vis / (value * 1e9),   # time the CPU path needs for the full step workload
+        "ms_per_step": 1e3 * secs / args.steps,         # measured: one bounded sample (see cpu_baseline.sample) per step
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
-        "config": {"workload": desc, "shape": [nbl * ncorr * args.gpus, m, n], **kw},
+        "config": make_config(args),
         "cpu_baseline": {"value": value, "unit": "GVis/s", "cores": procs, "kind": "port",
-                         "sample": f"{len(cube)} of {nbl * ncorr * args.gpus} matrices per step, one process per core, BLAS threads=1, "
+                         "sample": f"{len(cube)} matrices of {m} x {n} per step (a bounded sample of the step's "
+                                   f"{nbl * ncorr * CUBES_PER_STEP[args.workload] * args.gpus}), one process per core, BLAS threads=1, "
                                    f"one SVD evaluation per matrix (the reference as written does 3-5)"},
         "e2e": {"value": value, "unit": "GVis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -183,250 +239,492 @@ def log(msg):
         print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from visco_b200.engine import get_engine
+def measure_matmul_peaks(torch, dev):
+    """TF32 tensor-core and FP32 SIMT dense peaks by MEASURED_PEAKS.json's method: torch.matmul (cuBLAS), 2 N^3 flops,
+    best of 10 (burst) and back to back for ~1.5 s (sustained)."""
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32, N in (("tf32", True, 8192), ("fp32", False, 4096)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn((N, N), device=dev, dtype=torch.float32)
+            b = torch.randn((N, N), device=dev, dtype=torch.float32)
+            c = torch.empty_like(a)
+            for _ in range(3):
+                torch.matmul(a, b, out=c)
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b, out=c)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            reps = max(10, int(1500.0 / best))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            fl = 2.0 * N ** 3
+            out[name + "_tflops"] = fl / (best * 1e-3) / 1e12
+            out[name + "_tflops_sustained"] = fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            del a, b, c
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["how"] = "torch.matmul fp32 (allow_tf32 on: 8192^3; off: 4096^3), 2 N^3 flops, best of 10 (burst) and back to back ~1.5 s (sustained)"
+    return out
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    eng = get_engine(local)
 
-    nbl, ncorr, m, n, kw, desc = WORKLOADS[args.workload]
+def memcpy_ceiling(torch, dev, nbytes, seconds=0.6):
+    """Concurrent pinned H2D + D2H cudaMemcpyAsync of `nbytes` each on two streams, back to back: the host-link ceiling
+    of the e2e path on this box (GB/s per direction, both directions busy)."""
+    hin = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+    hin.zero_()
+    din = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    dout = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        torch.cuda.synchronize()
+        n = 0
+        t0 = time.perf_counter()
+        while True:
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+            n += 1
+            if n % 4 == 0:
+                torch.cuda.synchronize()
+                if time.perf_counter() - t0 > seconds:
+                    break
+        torch.cuda.synchronize()
+        res[mode] = n * nbytes / (time.perf_counter() - t0) / 1e9
+    return {"h2d_gbs": res["h2d"], "d2h_gbs": res["d2h"], "duplex_gbs_per_direction": res["both"]}
+
+
+def run_workload(eng, torch, dist, dev, world, rank, name, steps, warmup, sample_clocks=None):
+    """K steps of compress + reconstruct over resident cubes. Returns a dict of timings and the last cube's factors."""
+    nbl, ncorr, m, n, kw, desc = WORKLOADS[name]
     B = nbl * ncorr
-    A = torch.empty((B, m, n), dtype=torch.complex64, device=dev)
-    eng.synth_fill(A, nbl, ncorr, bl_offset=rank * nbl, nbl_total=nbl * world)
+    cps, ncubes = CUBES_PER_STEP[name], NCUBES[name]
+    cubes = []
+    for c in range(ncubes):
+        A = torch.empty((B, m, n), dtype=torch.complex64, device=dev)
+        # distinct data per cube and per rank: baseline offsets walk through one long synthetic array
+        eng.synth_fill(A, nbl, ncorr, bl_offset=(rank * ncubes + c) * nbl, nbl_total=nbl * world * ncubes)
+        cubes.append(A)
     kmax = eng.rank_bound(m, n, kw.get("compressionrank"), kw.get("decorrelation"))
     fac = (torch.empty((B, m, kmax), dtype=torch.complex64, device=dev), torch.empty((B, kmax), dtype=torch.float32, device=dev),
            torch.empty((B, kmax, n), dtype=torch.complex64, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
            torch.empty((B, 4), dtype=torch.float32, device=dev))
-    out = torch.empty_like(A)
+    out = torch.empty_like(cubes[0])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def one(i):
+        A = cubes[i % ncubes]
         U, S, Vt, ranks, stats = eng.compress(A, out=fac, kmax=kmax, **kw)
         eng.reconstruct(U, S, Vt, ranks, out=out)
 
-    log('warmup')
-    for _ in range(max(args.warmup, 0)):
-        step()
+    for s in range(max(warmup, 0)):
+        for c in range(cps):
+            one(s * cps + c)
     barrier()
-    log('timed region')
-
-    # ---- timed region: K steps, CUDA events on the launching stream, stage events recorded inside the library ----
-    eng.set_option("stage_timing", 1)
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
-    stage_acc, eig_acc = {}, {}
+    # ---- timed region: K steps, CUDA events on the launching stream ----
+    sampler = ClockSampler(sample_clocks) if sample_clocks is not None else None
+    if sampler:
+        sampler.start()
     launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        U, S, Vt, ranks, stats = eng.compress(A, out=fac, kmax=kmax, **kw)
-        ev[2 * i + 1].record()
-        eng.reconstruct(U, S, Vt, ranks, out=out)
-        ev[2 * i + 2].record()
-        for k_, v_ in eng.last_stage_ms().items():
-            stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
-        for k_, v_ in eng.last_eig_ms().items():
-            eig_acc[k_] = eig_acc.get(k_, 0.0) + v_
+    ev0.record()
+    for s in range(steps):
+        for c in range(cps):
+            one(s * cps + c)
+    ev1.record()
     barrier()
     launches = eng.launch_count - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
+    total_ms = ev0.elapsed_time(ev1)
+    # ---- stage split: a few more cubes with the library's own stage events (adds event records + syncs: not timed above)
+    eng.set_option("stage_timing", 1)
+    stage_acc, eig_acc, comp_ms, recon_ms = {}, {}, 0.0, 0.0
+    nst = min(8, max(2, cps))
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for i in range(nst):
+        A = cubes[i % ncubes]
+        e[0].record()
+        U, S, Vt, ranks, stats = eng.compress(A, out=fac, kmax=kmax, **kw)
+        e[1].record()
+        eng.reconstruct(U, S, Vt, ranks, out=out)
+        e[2].record()
+        e[2].synchronize()
+        comp_ms += e[0].elapsed_time(e[1]) / nst
+        recon_ms += e[1].elapsed_time(e[2]) / nst
+        for k_, v_ in eng.last_stage_ms().items():
+            stage_acc[k_] = stage_acc.get(k_, 0.0) + v_ / nst
+        for k_, v_ in eng.last_eig_ms().items():
+            eig_acc[k_] = eig_acc.get(k_, 0.0) + v_ / nst
     eng.set_option("stage_timing", 0)
-    total_ms = ev[0].elapsed_time(ev[-1])
-    comp_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
-    recon_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    last_cube = (nst - 1) % ncubes
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    nvis_all = float(B) * m * n * world
-    value = nvis_all / (ms_per_step * 1e-3) / 1e9
+    ms_per_step = total_ms / steps
+    return dict(name=name, B=B, m=m, n=n, kw=kw, desc=desc, kmax=kmax, cps=cps, ncubes=ncubes, ms_per_step=ms_per_step,
+                ms_per_cube=ms_per_step / cps, value=float(B) * m * n * cps * world / (ms_per_step * 1e-3) / 1e9,
+                launches=launches, clocks=clocks, stage_ms=stage_acc, eig_ms=eig_acc, comp_ms=comp_ms, recon_ms=recon_ms,
+                cubes=cubes, fac=fac, out=out, last_cube=last_cube)
 
-    log('gather')
+
+def stage_rooflines(w, kbar, pk, mm):
+    """Every stage of one cube against the roofline that bounds it. pk = MEASURED_PEAKS, mm = matmul peaks."""
+    B, m, n = w["B"], w["m"], w["n"]
+    r = min(m, n)
+    st, eg = w["stage_ms"], w["eig_ms"]
+    # the stages are timed inside a seconds-long loop at full load: the sustained peaks apply
+    tf32 = mm["tf32_tflops_sustained"]
+    fp32 = mm["fp32_tflops_sustained"]
+    out = {}
+    if st.get("gram", 0) > 0:
+        fl = 8.0 * r * r * max(m, n) * B
+        ach = fl / (st["gram"] * 1e-3) / 1e12
+        out["gram_tcgen05"] = {"bound": "tensor", "achieved": ach, "peak": tf32, "unit": "TFLOP/s", "frac": ach / tf32,
+                               "ms": st["gram"], "peak_source": "measured in this run: " + mm["how"] + " (sustained tf32)",
+                               "note": "algorithmic 8 r^2 max(m,n) flops, no credit for Hermitian symmetry or for the 3 TF32 "
+                                       "MMAs per product (3xTF32 caps this fraction at 1/3); tensor-pipe utilisation: profiles/"}
+    rb = algorithmic_bytes(B, m, n, kbar)
+    ach = rb / (w["recon_ms"] * 1e-3) / 1e9
+    out["reconstruct"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                          "ms": w["recon_ms"], "peak_source": pk["source"]}
+    if st.get("factors", 0) > 0:
+        ach = rb / (st["factors"] * 1e-3) / 1e9
+        out["factor_formation"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                   "frac": ach / pk["hbm_gbs"], "ms": st["factors"], "peak_source": pk["source"]}
+    eig_total = st.get("jacobi", 0.0) + st.get("small", 0.0)
+    if eig_total > 0:
+        # modelled flops of the direct solver: tridiagonalisation 16/3 r^3 (+ reflector accumulation 16/3 r^3 and the
+        # back-transformation GEMM 8 r^3 when all vectors are needed); latency / L2 bound at r = 256, see DESIGN
+        full = eg.get("reflectors", 0.0) > 0.05 * max(eig_total, 1e-9)
+        fl = B * (16.0 / 3.0 * r ** 3) * (2.0 if full else 1.0) + (B * 8.0 * r ** 3 * 2 if full else 0.0)
+        ach = fl / (eig_total * 1e-3) / 1e12
+        out["eigensolver"] = {"bound": "fp32-simt (modelled flops; no HBM/tensor roofline applies, SURVEY 8d)", "achieved": ach,
+                              "peak": fp32, "unit": "TFLOP/s", "frac": ach / fp32, "ms": eig_total,
+                              "kernels_ms": {k_: v_ for k_, v_ in eg.items() if v_ > 0},
+                              "peak_source": "measured in this run: cuBLAS fp32 (allow_tf32 off) 4096^3, sustained"}
+    return out
+
+
+def dominant_roofline(w, kbar, pk, share_of):
+    """The contract's `roofline`: the dominant kernel by time, SURVEY 8(d) algorithmic bytes of the compress pass per
+    launch over its CUDA-event duration, against the measured HBM peak."""
+    B, m, n = w["B"], w["m"], w["n"]
+    r = min(m, n)
+    eg, st = w["eig_ms"], w["stage_ms"]
+    cand = {"tridiag_kernel (Householder tridiagonalisation, one CTA per matrix)": eg.get("tridiag", 0.0),
+            "gram_tc_kernel (tcgen05 3xTF32 Gram product)": st.get("gram", 0.0),
+            "formq_kernel (reflector accumulation)": eg.get("reflectors", 0.0),
+            "factor formation (formv / cgemm_tc)": st.get("factors", 0.0),
+            "reconstruction (recon_smallk / cgemm_tc)": w["recon_ms"],
+            "jacobi_small kernel (one-sided Jacobi, whole matrix per CTA)": st.get("small", 0.0)}
+    top = max(cand, key=lambda q: cand[q])
+    t_ms = cand[top]
+    bytes_c = algorithmic_bytes(B, m, n, kbar)
+    key = f"{w['name']}:{top.split(' ')[0]}"
+    traffic, tsrc = ncu_traffic(key)
+    ach = bytes_c / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None
+    d = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+         "frac": ach / pk["hbm_gbs"] if ach else None, "traffic": traffic, "traffic_source": tsrc,
+         "avg_launch_ms": t_ms, "launches_per_cube": 1, "share_of_step": t_ms / share_of if share_of else None,
+         "algorithmic_bytes_per_launch": bytes_c, "peak_source": pk["source"],
+         "note": "SURVEY 8(d) Bytes_compress (A read once, factors written once) of the matrices one launch processes, over "
+                 "that kernel's CUDA-event time. "}
+    if top.startswith("tridiag"):
+        tri_bytes = 8.0 * B * sum((r - j - 1) * (r - j) / 2 for j in range(max(r - 2, 0)))
+        d["note"] += ("The kernel is not HBM bound at this size: it streams the trailing block of each r x r Gram matrix once "
+                      "per Householder step out of L2 (%.0f MB of Gram matrices per cube), %d dependent steps with four CTA "
+                      "barriers each; see roofline.stages.eigensolver for its modelled-flop rate against the measured FP32 "
+                      "peak. Minimal traffic of the algorithm itself (one read of the trailing lower triangle per step): "
+                      "%.2f GB per launch." % (B * r * r * 8 / 1e6, r - 2, tri_bytes / 1e9))
+        d["l2_algorithmic_gbs"] = tri_bytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None
+    return d
+
+
+def e2e_pipeline(Engine, torch, dist, dev, local, world, w, seconds=1.5):
+    """e2e through the host-buffer C ABI: E2E_THREADS host threads, each with its own handle, stream and pinned buffers,
+    each looping vk_compress_host -> vk_reconstruct_host on its own copy of the cube. Also one thread alone."""
+    B, m, n, kw, kmax = w["B"], w["m"], w["n"], w["kw"], w["kmax"]
+    per_mat = 8.0 * (2 * m * n + kmax * (m + n))
+    Be = int(max(1, min(B, 6e9 // per_mat)))
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
+
+    workers = []
+    for t in range(E2E_THREADS):
+        eng = Engine(local)
+        eng.host_stream = torch.cuda.Stream(device=dev)
+        Ah = pinned((Be, m, n), torch.complex64)
+        Ah[...] = w["cubes"][t % len(w["cubes"])][:Be].cpu().numpy()
+        hout = (pinned((Be, m, kmax), torch.complex64), pinned((Be, kmax), torch.float32), pinned((Be, kmax, n), torch.complex64),
+                pinned((Be,), torch.int32), pinned((Be, 4), torch.float32))
+        rec = pinned((Be, m, n), torch.complex64)
+        workers.append((eng, Ah, hout, rec))
+
+    def roundtrip(wk):
+        eng, Ah, hout, rec = wk
+        Uh, Sh, Vh, rh, _ = eng.compress_host(Ah, out=hout, **kw)
+        eng.reconstruct_host(Uh, Sh, Vh, rh, out=rec)
+
+    for wk in workers:
+        roundtrip(wk)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nthreads, per_thread):
+        errs = []
+
+        def loop(wk):
+            try:
+                for _ in range(per_thread):
+                    roundtrip(wk)
+            except Exception as ex:  # pragma: no cover
+                errs.append(ex)
+        ths = [threading.Thread(target=loop, args=(workers[i],)) for i in range(nthreads)]
+        barrier()
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), nthreads * per_thread
+
+    t1, n1 = timed(1, 3)
+    per = max(2, int(seconds / max(t1 / n1, 1e-4) / 1.0))     # round trips per thread for ~seconds of pipelined running
+    tp, npipe = timed(E2E_THREADS, per)
+    fac_bytes = int(sum(x.nbytes for x in workers[0][2][:4]))
+    vis = float(Be) * m * n * world
+    res = {"value": vis * npipe / tp / 1e9, "unit": "GVis/s", "matrices_per_call_per_gpu": Be,
+           "h2d_bytes_per_step": int((workers[0][1].nbytes + fac_bytes) * w["cps"]),
+           "d2h_bytes_per_step": int((fac_bytes + workers[0][2][4].nbytes + workers[0][3].nbytes) * w["cps"]),
+           "api": "vk_compress_host + vk_reconstruct_host (pinned host buffers, all copies inside the calls)",
+           "host_threads": E2E_THREADS, "round_trips_timed": npipe, "seconds": tp,
+           "single_thread_value": vis * n1 / t1 / 1e9,
+           "note": "one round trip = one cube up, factors down, factors up, cube down; %d host threads with a handle each "
+                   "(include/visco_b200.h: one handle per host thread) keep both PCIe directions and the GPU busy" % E2E_THREADS}
+    for eng, *_ in workers:
+        eng.close()
+    return res
+
+
+def extra_c5_sweep(eng, torch, dev, pk, seconds_cap=60.0):
+    """BASELINE configs[4]: 19701 baselines x 4 corr x 128 x 2048, decompression only, every k = 1..32. The 165 GB of
+    output stream through a ring of output buffers on one GPU (the factors of all 78 804 matrices stay resident)."""
+    import numpy as np
+    from oracle import visco_oracle as vo
+    B, m, n = 19701 * 4, 128, 2048
+    chunk = 4096
+    ring = [torch.empty((chunk, m, n), dtype=torch.complex64, device=dev) for _ in range(3)]
+    rows = []
+    t_start = time.perf_counter()
+    worst = 0.0
+    for k in range(1, 33):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + k)
+        U = torch.randn((B, m, k, 2), dtype=torch.float32, device=dev, generator=gen).mul_(1.0 / math.sqrt(2 * m))
+        Vt = torch.randn((B, k, n, 2), dtype=torch.float32, device=dev, generator=gen).mul_(1.0 / math.sqrt(2 * n))
+        U, Vt = torch.view_as_complex(U), torch.view_as_complex(Vt)
+        S = (100.0 * torch.exp(-0.2 * torch.arange(k, device=dev, dtype=torch.float32)))[None, :].repeat(B, 1).contiguous()
+
+        def sweep():
+            i = 0
+            for b0 in range(0, B, chunk):
+                b1 = min(B, b0 + chunk)
+                eng.reconstruct(U[b0:b1], S[b0:b1], Vt[b0:b1], None, out=ring[i % len(ring)][: b1 - b0])
+                i += 1
+        sweep()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        e0.record()
+        for _ in range(reps):
+            sweep()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        # oracle check of two matrices of the last ring slot written
+        nlast = B - (B - 1) // chunk * chunk
+        slot = ring[((B + chunk - 1) // chunk - 1) % len(ring)]
+        for j in (0, nlast - 1):
+            b = (B - 1) // chunk * chunk + j
+            ref = vo.ref_reconstruct_vis(U[b].cpu().numpy(), S[b].cpu().numpy(), Vt[b].cpu().numpy())
+            got = slot[j].cpu().numpy()
+            worst = max(worst, float(np.linalg.norm(got - ref) / np.linalg.norm(ref)))
+        by = algorithmic_bytes(B, m, n, k)
+        rows.append({"k": k, "ms": ms, "gvis_s": B * m * n / (ms * 1e-3) / 1e9, "gbs": by / (ms * 1e-3) / 1e9,
+                     "frac": by / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]})
+        del U, Vt, S
+        if time.perf_counter() - t_start > seconds_cap:
+            break
+    del ring
+    torch.cuda.empty_cache()
+    return {"workload": "configs[4]: 19701 bl x 4 corr x 128 x 2048 (78804 matrices, 165.3 GB of output per sweep), "
+                        "reconstruction only, k = 1..32; output ring of 3 x 4096 matrices, factors resident",
+            "bound": "hbm", "peak": pk["hbm_gbs"], "unit": "GB/s", "bytes": "SURVEY 8d Bytes_recon = 8mn + 8k(m+n) + 4k per matrix",
+            "min_frac": min(r_["frac"] for r_ in rows), "k_below_0.70": [r_["k"] for r_ in rows if r_["frac"] < 0.70],
+            "oracle_max_rel_frobenius_err": worst, "rows": [{k_: (round(v_, 4) if isinstance(v_, float) else v_) for k_, v_ in r_.items()} for r_ in rows]}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from visco_b200.engine import Engine, get_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_to_gpu_cpus(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    eng = get_engine(local)
+    pk = peaks()
+
+    log("main workload")
+    w = run_workload(eng, torch, dist, dev, world, rank, args.workload, args.steps, args.warmup, sample_clocks=local)
+
     # ---- the only collective: gather per-matrix ranks + statistics (after the timed region) ----
     from visco_b200.shard import gather_ranks_stats
-    rk, st = gather_ranks_stats(fac[3], fac[4])
+    rk, st = gather_ranks_stats(w["fac"][3], w["fac"][4])
     rk_h, st_h = rk.cpu().numpy(), st.cpu().numpy()
     kbar = float(rk_h.mean())
 
-    log('e2e')
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
-    def pinned(shape, dtype):
-        return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
-    # host buffers for the whole cube when they fit in ~8 GB of pinned memory, else a leading sub-batch (stated below)
-    per_mat = 8.0 * (2 * m * n + kmax * (m + n))
-    Be = int(max(1, min(B, 8e9 // per_mat)))
-    Ah = pinned((Be, m, n), torch.complex64)
-    Ah[...] = A[:Be].cpu().numpy()
-    hout = (pinned((Be, m, kmax), torch.complex64), pinned((Be, kmax), torch.float32), pinned((Be, kmax, n), torch.complex64),
-            pinned((Be,), torch.int32), pinned((Be, 4), torch.float32))
-    rec_h = pinned((Be, m, n), torch.complex64)
-    e2e_steps = max(1, min(args.steps, 5))
-
-    def e2e_step():
-        Uh, Sh, Vh, rh, _ = eng.compress_host(Ah, out=hout, **kw)
-        eng.reconstruct_host(Uh, Sh, Vh, rh, out=rec_h)
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    log("e2e")
+    e2e = e2e_pipeline(Engine, torch, dist, dev, local, world, w)
+    # the host-link ceiling of that path on this box, all ranks copying at once
+    cube_bytes = int(min(w["B"] * w["m"] * w["n"] * 8, 1 << 30))
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    fac_bytes = int(hout[0].nbytes + hout[1].nbytes + hout[2].nbytes + hout[3].nbytes)
-    e2e = {"value": float(Be) * m * n * world / e2e_s / 1e9, "unit": "GVis/s", "matrices_per_step_per_gpu": Be,
-           "h2d_bytes_per_step": int(Ah.nbytes + fac_bytes), "d2h_bytes_per_step": int(fac_bytes + hout[4].nbytes + rec_h.nbytes),
-           "api": "vk_compress_host + vk_reconstruct_host (pinned host buffers)", "steps": e2e_steps}
+        dist.barrier()
+    ceil = memcpy_ceiling(torch, dev, cube_bytes)
+    tc = torch.tensor([ceil["h2d_gbs"], ceil["d2h_gbs"], ceil["duplex_gbs_per_direction"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    tc = tc.cpu().numpy() / world
+    kw = w["kw"]
+    fac_frac = w["kmax"] * (w["m"] + w["n"]) / float(w["m"] * w["n"])      # factor bytes per matrix byte
+    ceiling_gvis = tc[2] * world / (8.0 * (1.0 + fac_frac))                # 8 B per visibility + factors, each direction
+    e2e.update({"memcpy_ceiling": {"h2d_gbs_per_gpu": float(tc[0]), "d2h_gbs_per_gpu": float(tc[1]),
+                                   "duplex_gbs_per_direction_per_gpu": float(tc[2]), "ranks_copying": world,
+                                   "how": "pinned cudaMemcpyAsync of one cube per direction on two streams, back to back, all ranks at once"},
+                "ceiling_gvis": float(ceiling_gvis), "frac_of_ceiling": float(e2e["value"] / ceiling_gvis) if ceiling_gvis else None,
+                "cpu_binding": binding})
 
+    # ---- other BASELINE configs in the same invocation (every rank runs its shard; rank 0 reports) ----
+    others = {}
+    main_cubes_sample = None
+    if rank == 0:
+        procs = len(os.sched_getaffinity(0))
+        nsample = cpu_sample_size(w["B"], w["m"], w["n"], procs)
+        idx = np.linspace(0, w["B"] - 1, nsample).astype(int)
+        main_cubes_sample = (idx, w["cubes"][w["last_cube"]][torch.as_tensor(idx, device=dev)].cpu().numpy())
+        fac_h = tuple(x.cpu().numpy() for x in w["fac"][:3])
+    main = {k_: v_ for k_, v_ in w.items() if k_ not in ("cubes", "fac", "out")}
+    del w
+    torch.cuda.empty_cache()
+    if args.extras:
+        for name in ("meerkat", "small"):
+            if name == args.workload:
+                continue
+            log("extra " + name)
+            steps_x = 4 if name == "meerkat" else 6
+            x = run_workload(eng, torch, dist, dev, world, rank, name, steps_x, 2)
+            xrk, xst = gather_ranks_stats(x["fac"][3], x["fac"][4])
+            xk = float(xrk.float().mean().item())
+            conv = bool((xst[:, 3] == 1).all().item())
+            x = {k_: v_ for k_, v_ in x.items() if k_ not in ("cubes", "fac", "out")}
+            torch.cuda.empty_cache()
+            if rank == 0:
+                others[name] = {"workload": x["desc"], "n_gpus": world, "value_gvis_s": x["value"], "ms_per_cube": x["ms_per_cube"],
+                                "shape_per_gpu": [x["B"], x["m"], x["n"]], **x["kw"], "mean_rank": xk, "converged": conv,
+                                "steps": steps_x, "compress_ms": x["comp_ms"], "reconstruct_ms": x["recon_ms"],
+                                "stage_ms": x["stage_ms"], "eig_ms": x["eig_ms"], "_x": x}
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- rooflines (rank 0's kernels; algorithmic work per SURVEY section 8d) ----
-    pk = peaks()
-    r = min(m, n)
-    stage_ms = {k_: v_ / args.steps for k_, v_ in stage_acc.items()}
-    tf32_peak = 0.5 * pk["bf16_tflops"]
-    stages = {}
-    if stage_ms.get("gram", 0) > 0:
-        fl = 8.0 * r * r * max(m, n) * B
-        ach = fl / (stage_ms["gram"] * 1e-3) / 1e12
-        stages["gram_tcgen05"] = {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                                  "ms": stage_ms["gram"], "note": "algorithmic 8 r^2 n flops (no credit for the 3 TF32 MMAs per product); "
-                                  "peak = 0.5 x measured dense bf16 (TF32 rate); stage time includes the Gram normalisation pass"}
-    rb = algorithmic_bytes(B, m, n, kbar)
-    ach = rb / (recon_ms * 1e-3) / 1e9
-    stages["reconstruct"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "ms": recon_ms}
-    fb = algorithmic_bytes(B, m, n, kbar)
-    if stage_ms.get("factors", 0) > 0:
-        ach = fb / (stage_ms["factors"] * 1e-3) / 1e9
-        stages["factor_formation"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                                      "ms": stage_ms["factors"]}
-    jac_ms = stage_ms.get("jacobi", 0.0) + stage_ms.get("small", 0.0)
-    sweeps = float(st_h[:, 2].mean())
-    eig_ms = {k_: v_ / args.steps for k_, v_ in eig_acc.items()}
-    if sum(eig_ms.values()) > 0:
-        # direct eigensolver (tridiag.cu). Its kernels, by time; the dominant one is reported as `roofline`.
-        #  tridiag_kernel: streams the trailing block once per Householder step (read + write): HBM roofline,
-        #      algorithmic bytes = B * sum_j (r-j-1)^2 * 16; served from L2 when B r^2 8 bytes fit there.
-        #  leading pairs / QL: scalar, latency bound (one lane per eigenvalue / per matrix): no roofline.
-        #  rotations: shared-memory bound (one load + one store of 16 bytes per rotation and column pair).
-        # matrices per internal pass of the direct solver (api.cu:auto_chunk: 8 GB of scratch)
-        per = 2 * r * r * 8 + (1.5 * r * r + 256) * 8 + (8 * r + 64) * 80 + 2 * 32 * r * 4 + 6 * r * 4
-        eig_chunk = int(min(B, max(1, (8 << 30) // per)))
-        tb = 16.0 * B * sum((r - j - 1) ** 2 for j in range(max(r - 2, 0)))
-        t_ms = eig_ms.get("tridiag", 0.0)
-        tri = {"bound": "hbm", "kernel": "tridiag_kernel (Householder tridiagonalisation, fused rank-2 update + matvec)",
-               "achieved": tb / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
-               "frac": tb / (t_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if t_ms > 0 else None,
-               # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full): the KAT-7 cube as captured;
-               # MeerKAT: 181.2 GB for a 296-matrix launch, scaled to the matrices of this launch
-               "traffic": {"kat7": 194.4e6, "meerkat": 181.2e9 / 296 * min(B, eig_chunk)}.get(args.workload),
-               "traffic_source": {"kat7": "profiles/r01_ncu_full_tridiag_kat7.txt",
-                                  "meerkat": "profiles/r01_ncu_full_tridiag_r512.txt"}.get(args.workload),
-               "avg_launch_ms": t_ms / max(1.0, math.ceil(B / max(1, eig_chunk))), "ms": t_ms,
-               "launches_per_step": float(max(1, math.ceil(B / max(1, eig_chunk)))),
-               "share_of_step": t_ms / ms_per_step if ms_per_step else None,
-               "algorithmic_bytes_per_step": tb,
-               "note": "algorithmic bytes = trailing block read + written once per Householder step; "
-                       + ("the %d matrices of a pass (%.0f MB) stay in the 126 MB L2, so DRAM traffic is far below it and the "
-                          "figure is an L2-bandwidth one" % (min(B, eig_chunk), min(B, eig_chunk) * r * r * 8 / 1e6)
-                          if min(B, eig_chunk) * r * r * 8 < 126e6 else
-                          "the matrices of a pass (%.0f MB) exceed L2: HBM-bound" % (min(B, eig_chunk) * r * r * 8 / 1e6)),
-               "peak_source": pk["source"]}
-        stages["eig_tridiag"] = tri
-        for k_, label in (("leading_pairs", "bisect/twisted/backtr kernels (leading eigenpairs, fixed rank)"),
-                          ("ql", "tql_kernel (implicit QL, one lane per matrix, latency bound)"),
-                          ("reflectors", "formq_kernel (reflector accumulation, rows in registers, fp32 SIMT)"),
-                          ("rotations", "rotapply_kernel (level-scheduled plane rotations, shared-memory bound)")):
-            if eig_ms.get(k_, 0.0) > 0:
-                stages["eig_" + k_] = {"kernel": label, "ms": eig_ms[k_], "share_of_step": eig_ms[k_] / ms_per_step}
-        top = max(eig_ms, key=lambda q: eig_ms[q])
-        if top == "tridiag":
-            dominant = tri
-        else:
-            dominant = {"bound": "hbm", "kernel": stages["eig_" + top]["kernel"], "achieved": None, "peak": pk["hbm_gbs"],
-                        "unit": "GB/s", "frac": None, "traffic": None, "ms": eig_ms[top],
-                        "share_of_step": eig_ms[top] / ms_per_step,
-                        "note": "not an HBM- or tensor-bound kernel (see roofline_stages.eig_tridiag for the HBM-bound one); "
-                                "time only", "peak_source": pk["source"]}
-    else:
-        # the Jacobi rotation kernels. FP32 SIMT + shared memory: neither contract roofline bounds it
-        # (SURVEY 8d); reported against HBM with its algorithmic traffic (every launch reads and writes the r x r vectors).
-        if eng.uses_small_path(m, n):
-            L = max(m, n) + r
-            jbytes = 2.0 * B * r * L * 8
-            nlaunch = 1.0
-        else:
-            jbytes = 2.0 * B * r * r * 8
-            nb = 2 if r <= 64 else ((r + 15) // 16 + ((r + 15) // 16) % 2)
-            nlaunch = max(1.0, sweeps * nb)
-        dom_ms = jac_ms / nlaunch if jac_ms > 0 else 0.0
-        dominant = {"bound": "hbm", "kernel": "jacobi (one-sided cyclic Jacobi rotations, fp32 SIMT)",
-                    "achieved": (jbytes / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else None, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": (jbytes / (dom_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if dom_ms > 0 else None,
-                    "traffic": None, "avg_launch_ms": dom_ms, "launches_per_step": nlaunch,
-                    "share_of_step": jac_ms / ms_per_step if ms_per_step else None,
-                    "modelled_gflop_per_step": 22.0 * r ** 3 * sweeps * B / 1e9 if not eng.uses_small_path(m, n) else None,
-                    "note": "latency/issue-bound fp32 rotations on L2-resident data; no HBM or tensor roofline applies, frac is informational",
-                    "peak_source": pk["source"]}
+    log("matmul peaks")
+    mm = measure_matmul_peaks(torch, dev)
+    stages = stage_rooflines(main, kbar, pk, mm)
+    dominant = dominant_roofline(main, kbar, pk, main["ms_per_cube"])
+    for name, o in others.items():
+        x = o.pop("_x")
+        o["stages"] = stage_rooflines(x, o["mean_rank"], pk, mm)
+    if args.extras:
+        log("C5 sweep")
+        others["ska_c5_sweep"] = extra_c5_sweep(eng, torch, dev, pk)
+    dominant["stages"] = stages
+    dominant["other_workloads"] = others
+    dominant["measured_peaks"] = {**{k_: v_ for k_, v_ in mm.items()}, "hbm_gbs": pk["hbm_gbs"], "hbm_source": pk["source"]}
 
-    log('cpu baseline')
-    # ---- CPU baseline on the host cores: oracle port on a bounded sample of THIS cube (bit-identical inputs) ----
-    procs = len(os.sched_getaffinity(0))
-    per_matrix_s = 2.5e-9 * m * n * r
-    nsample = int(max(min(B, 20.0 / max(per_matrix_s, 1e-6)), min(B, procs)))
-    idx = np.linspace(0, B - 1, nsample).astype(int)
-    sample = A[torch.as_tensor(idx, device=dev)].cpu().numpy()
-    cpu_rate, cpu_s = cpu_roundtrip_rate(sample, kw, procs)
-    # parity spot check of the benchmarked result against the oracle on three matrices of the sample
+    log("cpu baseline")
+    # ---- CPU baseline on the host cores: oracle port on a bounded sample of the benchmarked cube (bit-identical inputs) ----
+    idx, sample = main_cubes_sample
+    cpu_rate, cpu_s, _ = cpu_roundtrip_rate(sample, kw, procs)
     from oracle import visco_oracle as vo
-    Uh, Sh, Vh = fac[0].cpu().numpy(), fac[1].cpu().numpy(), fac[2].cpu().numpy()
     s_err = 0.0
-    for b in idx[:3]:
+    for j, b in enumerate(idx[:3]):
         k = int(rk_h[b])
-        u, s, vt = vo.ref_apply_svd(sample[list(idx).index(b)], kw.get("decorrelation"), kw.get("compressionrank"))
+        u, s, vt = vo.ref_apply_svd(sample[j], kw.get("decorrelation"), kw.get("compressionrank"))
         kk = min(k, len(s))
-        s_err = max(s_err, float(np.max(np.abs(Sh[b, :kk] - s[:kk]) / s[:kk])))
+        s_err = max(s_err, float(np.max(np.abs(fac_h[1][b, :kk] - s[:kk]) / s[:kk])))
     cpu_baseline = {"value": cpu_rate / 1e9, "unit": "GVis/s", "cores": procs, "kind": "port",
-                    "sample": f"{nsample} of {B} matrices of this cube (D2H copies, bit-identical inputs), one process per core, "
-                              f"BLAS threads=1, one SVD evaluation per matrix; {cpu_s:.1f} s",
+                    "sample": f"{len(idx)} of {main['B']} matrices of the last cube processed (D2H copies, bit-identical inputs), one "
+                              f"process per core, BLAS threads=1, one SVD evaluation per matrix; {cpu_s:.1f} s",
                     "sigma_max_rel_err_vs_oracle": s_err}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "GVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "complex64 (fp32 arithmetic; Gram as 3xTF32 on tcgen05 with fp32 accumulation)", "data": "synthetic",
-        "config": {"workload": desc, "shape_per_gpu": [B, m, n], **kw,
-                   "l2": f"inputs {A.numel() * 8 / 1e6:.0f} MB per GPU " + ("> 126 MB L2 (no flush needed)" if A.numel() * 8 > 126e6 else "< L2"),
-                   "mean_rank": kbar, "mean_sweeps": sweeps, "converged": bool(st_h[:, 3].min() == 1)},
-        "compress_ms": comp_ms, "reconstruct_ms": recon_ms, "stage_ms": stage_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": dominant, "roofline_stages": stages, "cpu_baseline": cpu_baseline,
+        "metric": METRIC, "value": main["value"], "unit": "GVis/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "complex64 (fp32 arithmetic; Gram and large-rank GEMMs as 3xTF32 on tcgen05 with fp32 accumulation)",
+        "data": "synthetic",
+        "config": make_config(args),
+        "run": {"ms_per_cube": main["ms_per_cube"], "distinct_cubes_resident": main["ncubes"],
+                "l2": f"each cube is {main['B'] * main['m'] * main['n'] * 8 / 1e6:.0f} MB and {main['ncubes']} rotate: inputs come from HBM "
+                      "(126 MB L2), no flush needed",
+                "mean_rank": kbar, "converged": bool(st_h[:, 3].min() == 1), "compress_ms": main["comp_ms"],
+                "reconstruct_ms": main["recon_ms"], "stage_ms": main["stage_ms"], "eig_ms": main["eig_ms"]},
+        "clocks": main["clocks"], "e2e": e2e, "gpu_launches": int(main["launches"]),
+        "roofline": dominant, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -434,10 +732,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="kat7", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--extras", type=int, default=1, help="also measure the other BASELINE configs (C3 shard, C4, C5 sweep)")
     ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_worker:
@@ -451,7 +750,8 @@ def main():
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
-               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload]
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup), "--workload", args.workload,
+               "--extras", str(args.extras)]
         return subprocess.call(cmd)
     return run_ours(args)
 

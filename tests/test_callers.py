@@ -60,8 +60,10 @@ def test_cli_surface_matches_the_reference():
     defaults = {o[0]: o[3] for o in COMPRESS_OPTIONS}
     assert defaults["compressor"] == "zstd" and defaults["level"] == 4 and defaults["batch_size"] == 20
     assert defaults["correlation"] == "XX,YY" and defaults["outcolumn"] == "COMPRESSED_DATA"
+    # the reference's four options with its defaults, plus the additive --ngpus (default 1 = the reference's behaviour)
     assert {o[0]: o[3] for o in DECOMPRESS_OPTIONS} == {"zarrstore": None, "ms": "decompressed.ms",
-                                                        "column": "COMPRESSED_DATA", "batch_size": 50}
+                                                        "column": "COMPRESSED_DATA", "batch_size": 50, "ngpus": 1}
+    assert defaults["ngpus"] == 1 and abbr["ngpus"] == "ng"
     r = CliRunner()
     out = r.invoke(cli, ["--help"])
     assert out.exit_code == 0 and "compressms" in out.output and "decompressms" in out.output

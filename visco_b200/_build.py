@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvisco_b200.so")
-SOURCES = ["api.cu", "jacobi.cu", "stages.cu", "gram_tc.cu", "layout.cu", "cgemm_tc.cu", "topk.cu", "tridiag.cu"]
+SOURCES = ["api.cu", "jacobi.cu", "stages.cu", "gram_tc.cu", "layout.cu", "cgemm_tc.cu", "topk.cu", "tridiag.cu", "recon_tc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC", "-cudart", "static", "--threads", "8"]
 

@@ -116,21 +116,27 @@ def _leaf_jobs(vis, baseline_batch, correlation, correlation_optimized):
 
 def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_optimized=False, decorrelation=None,
                      compressionrank=None, outcolumn="COMPRESSED_DATA", compressor="zstd", level=4, batch_size=20,
-                     antennas=None, data_dev=None):
+                     antennas=None, data_dev=None, ngpus=1):
     """Compress every (baseline, correlation) matrix of `vis` (a visco_b200.msdata.VisData) and write the leaf tree
     ``<zarr>/MAIN/<outcolumn>/<ANT1>&<ANT2>/<corr>/`` (reference compress_visdata, compress_ms.py:389-703).
 
     Device pipeline: the visibility column is uploaded once; per batch of baselines the row indices go to the GPU,
     vk_gather_baselines builds the [B, time, chan] cube (all selected correlations in one pass over the rows,
     including the --correlation-optimized vstack), vk_compress_batched factorises it, and only the truncated factors
-    come back to the host to be written as leaves. Returns the number of baselines processed."""
+    come back to the host to be written as leaves.
+
+    ngpus > 1: the baselines are split with shard.shard_baselines into one contiguous range per GPU; one host thread per
+    GPU (its own vk_handle) runs the same batch loop on its range and writes its leaves concurrently - the role of the
+    reference's ``nworkers`` dask processes (compress_ms.py:571-697, visco/__init__.py:35-89). No data-path collective.
+    Returns the number of baselines processed."""
+    import threading
     from pathlib import Path
 
     import torch
 
+    from .engine import Engine
+    from .shard import shard_baselines
     from .zarr_leaf import write_svd_to_zarr
-    eng = get_engine()
-    dev = f"cuda:{eng.device}"
     corr_names = [c.strip() for c in correlation.split(",") if c.strip()]
     if correlation_optimized:
         # XX+YY -> "diagonals", XY+YX -> "offdiagonals"; the reference hard-codes enums 9/12 and 10/11 (:600-657)
@@ -147,33 +153,58 @@ def compress_visdata(vis, zarr_output_path, correlation="XX,YY", correlation_opt
     baselines = vis.baselines(antennas)
     if not leaf_names:
         return 0
-    if data_dev is None:
-        data_dev = torch.from_numpy(vis.data).to(dev)
-    processed = 0
-    for batch in batch_baselines(baselines, batch_size):
-        by_m = {}
-        for a1, a2 in batch:
-            rows = vis.baseline_rows(int(a1), int(a2))
-            if rows.size:
-                by_m.setdefault(rows.size, []).append((int(a1), int(a2), rows))
-        for m, ents in by_m.items():           # baselines of a batch may have different numbers of rows
-            row_idx = torch.from_numpy(np.stack([e[2] for e in ents]).astype(np.int32)).to(dev)
-            corr_sel = torch.tensor([sel] * len(ents), dtype=torch.int32, device=dev)
-            cube = eng.gather_baselines(data_dev, row_idx, corr_sel, stack)
-            U, S, Vt, ranks, stats = eng.compress(cube, decorrelation, compressionrank)
-            Uh, Sh, Vh, rk, st = (x.cpu().numpy() for x in (U, S, Vt, ranks, stats))
-            if not np.all(st[:, 3] == 1):
-                raise np.linalg.LinAlgError("SVD did not converge")
-            for e, (a1, a2, rows) in enumerate(ents):
-                name = f"{vis.antenna_names[a1]}&{vis.antenna_names[a2]}"
-                rowid = np.tile(vis.rowid[rows], stack)
-                for j, leaf_name in enumerate(leaf_names):
-                    b = e * len(leaf_names) + j
-                    k = int(rk[b])
-                    leaf = Path(zarr_output_path) / "MAIN" / f"{outcolumn}" / name / leaf_name
-                    write_svd_to_zarr((Uh[b, :, :k], Sh[b, :k], Vh[b, :k, :]), leaf, compressor, level, rowid)
-        processed += len(batch)
-    return processed
+
+    def run(eng, my_baselines, data_dev):
+        dev = f"cuda:{eng.device}"
+        with torch.cuda.device(eng.device):
+            if data_dev is None:
+                data_dev = torch.from_numpy(vis.data).to(dev)
+            done = 0
+            for batch in batch_baselines(my_baselines, batch_size):
+                by_m = {}
+                for a1, a2 in batch:
+                    rows = vis.baseline_rows(int(a1), int(a2))
+                    if rows.size:
+                        by_m.setdefault(rows.size, []).append((int(a1), int(a2), rows))
+                for m, ents in by_m.items():           # baselines of a batch may have different numbers of rows
+                    row_idx = torch.from_numpy(np.stack([e[2] for e in ents]).astype(np.int32)).to(dev)
+                    corr_sel = torch.tensor([sel] * len(ents), dtype=torch.int32, device=dev)
+                    cube = eng.gather_baselines(data_dev, row_idx, corr_sel, stack)
+                    U, S, Vt, ranks, stats = eng.compress(cube, decorrelation, compressionrank)
+                    Uh, Sh, Vh, rk, st = (x.cpu().numpy() for x in (U, S, Vt, ranks, stats))
+                    if not np.all(st[:, 3] == 1):
+                        raise np.linalg.LinAlgError("SVD did not converge")
+                    for e, (a1, a2, rows) in enumerate(ents):
+                        name = f"{vis.antenna_names[a1]}&{vis.antenna_names[a2]}"
+                        rowid = np.tile(vis.rowid[rows], stack)
+                        for j, leaf_name in enumerate(leaf_names):
+                            b = e * len(leaf_names) + j
+                            k = int(rk[b])
+                            leaf = Path(zarr_output_path) / "MAIN" / f"{outcolumn}" / name / leaf_name
+                            write_svd_to_zarr((Uh[b, :, :k], Sh[b, :k], Vh[b, :k, :]), leaf, compressor, level, rowid)
+                done += len(batch)
+        return done
+
+    ngpus = max(1, min(int(ngpus or 1), torch.cuda.device_count(), max(1, len(baselines))))
+    if ngpus == 1:
+        return run(get_engine(), baselines, data_dev)
+    results, errors = [0] * ngpus, []
+
+    def worker(g):
+        try:
+            off, cnt = shard_baselines(len(baselines), ngpus, g)
+            eng = get_engine(g) if g == torch.cuda.current_device() else Engine(g)
+            results[g] = run(eng, baselines[off:off + cnt], data_dev if (data_dev is not None and data_dev.device.index == g) else None)
+        except BaseException as ex:          # re-raised in the caller's thread
+            errors.append(ex)
+    threads = [threading.Thread(target=worker, args=(g,)) for g in range(ngpus)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return sum(results)
 
 
 def write_store_tables(zarr_path, vis, column="DATA", outcolumn="COMPRESSED_DATA"):
@@ -223,10 +254,11 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
                      scan: int = 1, column: str = "DATA", outcolumn: str = "COMPRESSED_DATA", batch_size: int = 20,
                      dashboard_addr: str = None, host_addr: str = None, use_model_data: bool = False,
                      model_data: str = None, flag_estimate: bool = False, decorrelation: float = None,
-                     compressionrank: int = None, flagvalue: int = None, antennas: list = None):
+                     compressionrank: int = None, flagvalue: int = None, antennas: list = None, ngpus: int = 1):
     """Same keyword arguments as the reference's compress_full_ms (compress_ms.py:782-811). The dask-cluster arguments
     (nworkers, nthreads, memory_limit, direct_to_workers, dashboard_addr, host_addr, chunk_size_row) are accepted and
-    ignored: the batches run on the GPU of this process. Flags are bit-packed into the FLAGS / FLAGS_ROW groups and
+    ignored: the batches run on the GPU(s) of this process - `ngpus` (additive keyword, default 1) spreads the baselines
+    over that many GPUs of the box, one host thread and handle each (see compress_visdata). Flags are bit-packed into the FLAGS / FLAGS_ROW groups and
     flagged visibilities are replaced by model data or by a constant on the device (compress_ms.py:478-483, 530-562);
     the scipy-griddata estimator (flag_estimate, compress_ms.py:197-292) is out of scope and raises."""
     import os
@@ -287,4 +319,4 @@ def compress_full_ms(ms_path: str, zarr_path: str, consolidated: bool = True, ch
         LOG.warning("No flag replacement specified - flagged data will not be replaced")  # reference :566
     return compress_visdata(vis, zarr_path, data_dev=data_dev, correlation=correlation, correlation_optimized=correlation_optimized,
                             decorrelation=decorrelation, compressionrank=compressionrank, outcolumn=outcolumn,
-                            compressor=compressor, level=level, batch_size=batch_size, antennas=antennas)
+                            compressor=compressor, level=level, batch_size=batch_size, antennas=antennas, ngpus=ngpus)

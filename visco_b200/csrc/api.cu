@@ -398,6 +398,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->topk = (int)v;
     else if (k == "gemm_impl")
         h->gemm_impl = (int)v;
+    else if (k == "recon_tc_impl")
+        h->recon_tc_impl = (int)v;
     else if (k == "recon_generic")
         h->recon_generic = (int)v;
     else if (k == "small_reg")
@@ -406,6 +408,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->jacobi_generic = (int)v;
     else if (k == "eig_impl")
         h->eig_impl = (int)v;
+    else if (k == "tridiag_impl")
+        h->tridiag_impl = (int)v;
     else if (k == "eigvec_impl")
         h->eigvec_impl = (int)v;
     else if (k == "ql_maxit")

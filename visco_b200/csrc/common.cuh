@@ -41,10 +41,12 @@ struct vk_context {
     int chunk = 0;  // matrices per internal pass, 0 = auto
     int topk = 0;            // 0 = auto (subspace iteration for compressionrank <= 4), 1 = full Jacobi only, 2 = up to rank 8
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
+    int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
     int jacobi_generic = 0;  // 1 = never use the register-resident cross kernel (debug / comparison)
     int eig_impl = 0;        // 0 = auto, 1 = cyclic Jacobi, 2 = tridiagonalisation + implicit QL (tridiag.cu)
+    int tridiag_impl = 0;    // 0 = auto (deferred updates for 384 < r <= 512), 1 = update every step, 2 = deferred updates also for 128 < r <= 256
     int eigvec_impl = 0;     // eigenvectors of T on the full path: 0 = twisted factorisation + Newton-Schulz + GEMMs, 1 = implicit QL
     int ql_maxit = 60;       // QL iterations allowed per eigenvalue (tests lower it to exercise the Jacobi fallback)
     int64_t eig_fallbacks = 0;  // internal passes the direct solver handed back to the Jacobi solver
@@ -162,6 +164,9 @@ int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const flo
                        int B, int m, int n, int kmax);
 int vk_launch_cgemm_tc_plain(vk_context* h, const float2* P, const float2* Q, float2* D, const float* rowscale, int B,
                              int M, int N, int K);
+bool vk_recon_tc_supported(int m, int n, int kmax);
+int vk_launch_recon_tc_smallk(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks,
+                              float2* out, int B, int m, int n, int kmax);
 int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const float2* Vt, const int32_t* ranks, int B,
                           int m, int n, int kmax, float2* out);
 int vk_launch_synth(vk_context* h, float2* A, int nbl_local, int ncorr, int m, int n, int bl_offset, int nbl_total,

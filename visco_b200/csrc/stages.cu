@@ -898,6 +898,9 @@ int vk_launch_reconstruct(vk_context* h, const float2* U, const float* S, const 
     // small rank: dedicated streaming kernel (modes >= ranks[b] are skipped, as on the other two paths)
     const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(Vt) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
     // (k <= 16 stays below the FFMA2 limit of ~0.7 x HBM; the tcgen05 GEMM only wins from k ~ 20 on, measured)
+    if (aligned && h->recon_tc_impl == 0 && !h->recon_generic && vk_recon_tc_supported(m, n, kmax) &&
+        (reinterpret_cast<uintptr_t>(U) % 8) == 0)
+        return vk_launch_recon_tc_smallk(h, U, S, Vt, ranks, out, B, m, n, kmax);   // 8 < k <= 32: persistent tcgen05 kernel
     if (aligned && kmax <= 16 && !h->recon_generic) {
         if (kmax <= 2) return launch_recon_smallk<2>(h, U, S, Vt, ranks, B, m, n, kmax, out);
         if (kmax <= 4) return launch_recon_smallk<4>(h, U, S, Vt, ranks, B, m, n, kmax, out);

@@ -539,6 +539,330 @@ __global__ void __launch_bounds__(TD_THREADS, 1)
     }
 }
 
+
+// ---- 1d. full-storage reduction with DEFERRED updates while the trailing block lives in global memory (L2 / HBM), then
+//          the shared-memory resident steps of kernel 1. The streaming phase of kernel 1 reads AND writes the trailing
+//          block every step and is bound by the L2 throughput an SM gets (r = 256) or by HBM (r = 512); here up to NB
+//          reflector pairs (v_s, w_s) stay pending in shared memory (LAPACK latrd): a step only READS the block as the
+//          last update pass left it (A0) and corrects the product,
+//              A v = A0 v - sum_s [ v_s (w_s^H v) + w_s (v_s^H v) ],
+//          and the row that defines the next reflector is corrected the same way; when NB pairs are pending the pass of
+//          the next step applies them all (rank-2NB update, read + write) before its product. Whole rows, whole columns:
+//          no triangle bookkeeping, the reflector's entries for a lane's columns stay in registers for the pass, and RB
+//          rows share every shared-memory operand of the update. Bytes per step: (1 + 2/NB)/2 of kernel 1. -------------
+template <int EPL, int RB, int NB>
+__global__ void __launch_bounds__(TD_THREADS, 1)
+    tridiag_defer_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
+                         float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
+    constexpr int WD = EPL * 32;
+    static_assert(NB <= TD_WARPS, "one warp per pending pair computes its two inner products");
+    extern __shared__ float2 td_sm[];
+    float2* vprev = td_sm;            // resident phase only: pending single pair (vprev, wv)
+    float2* vnew = td_sm + WD;
+    float2* wv = td_sm + 2 * WD;
+    float2* pv = td_sm + 3 * WD;
+    float2* nrow = td_sm + 4 * WD;    // row j+1 as memory (or T) holds it after the pass of step j
+    float2* Vp = td_sm + 5 * WD;      // [NB][WD] pending reflectors (streaming phase)
+    float2* Wp = Vp + NB * WD;        // [NB][WD] pending w vectors
+    float2* T = Wp + NB * WD;         // [ts][ts] trailing block once it fits (ts <= nts): rows/cols j0 .. r-1
+    int j0 = -1, ts = 0;
+    __shared__ float s_part[TD_WARPS];
+    __shared__ float2 s_kpart[TD_WARPS];
+    __shared__ float2 s_alpha;
+    __shared__ float2 s_ab[2 * NB];   // alpha_s = w_s^H v, beta_s = v_s^H v
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* M = Wall + (size_t)b * wstride;
+    float* d = dall + (size_t)b * r;
+    float* e = eall + (size_t)b * r;
+    float* taus = tauall + (size_t)b * r;
+    float2* ph = phall + (size_t)b * r;
+    float2 phase = make_float2(1.f, 0.f);
+    if (tid == 0) ph[0] = phase;
+    for (int k = tid; k < (5 + 2 * NB) * WD; k += TD_THREADS) td_sm[k] = make_float2(0.f, 0.f);
+    __syncthreads();
+    int P = 0;  // pending pairs of the streaming phase (uniform)
+
+    for (int j = 0; j + 2 < r; ++j) {
+        const int e0 = (j + 1) >> 5;
+        if (j0 < 0 && r - j <= nts) {
+            // from here on the trailing block lives in shared memory, with every pending pair applied on the way in
+            j0 = j, ts = r - j;
+            for (int idx = tid; idx < ts * ts; idx += TD_THREADS) {
+                const int i = j0 + idx / ts, k = j0 + idx % ts;
+                float2 x = M[(size_t)i * ld + k];
+                for (int s2 = 0; s2 < P; ++s2) {
+                    const float2 vi = Vp[s2 * WD + i], wi = Wp[s2 * WD + i], vk = Vp[s2 * WD + k], wk = Wp[s2 * WD + k];
+                    x.x -= vi.x * wk.x + vi.y * wk.y + wi.x * vk.x + wi.y * vk.y;
+                    x.y -= vi.y * wk.x - vi.x * wk.y + wi.y * vk.x - wi.x * vk.y;
+                }
+                T[idx] = x;
+            }
+            __syncthreads();
+            for (int k = j + tid; k < r; k += TD_THREADS) nrow[k] = T[k - j0];   // row j of the updated block
+            for (int k = tid; k < WD; k += TD_THREADS) vprev[k] = wv[k] = make_float2(0.f, 0.f);
+            P = 0;
+            __syncthreads();
+        }
+        const bool resident = j0 >= 0;
+        // row j with everything pending applied: diagonal d_j and the column below it (a = conj(row))
+        float ss = 0.f;
+        {
+            const float2 v0 = vprev[j], w0 = wv[j];  // zero outside the resident phase
+            for (int k = tid; k < WD; k += TD_THREADS) {
+                float2 a = make_float2(0.f, 0.f);
+                if (k >= j && k < r) {
+                    float2 x = (j == 0) ? M[k] : nrow[k];
+                    if (resident) {
+                        const float2 wk = wv[k], vk = vprev[k];
+                        x.x -= v0.x * wk.x + v0.y * wk.y + w0.x * vk.x + w0.y * vk.y;
+                        x.y -= v0.y * wk.x - v0.x * wk.y + w0.y * vk.x - w0.x * vk.y;
+                    } else {
+                        for (int s2 = 0; s2 < P; ++s2) {
+                            const float2 vj = Vp[s2 * WD + j], wj = Wp[s2 * WD + j], vk = Vp[s2 * WD + k], wk = Wp[s2 * WD + k];
+                            x.x -= vj.x * wk.x + vj.y * wk.y + wj.x * vk.x + wj.y * vk.y;
+                            x.y -= vj.y * wk.x - vj.x * wk.y + wj.y * vk.x - wj.x * vk.y;
+                        }
+                    }
+                    if (k == j) {
+                        d[j] = x.x;
+                    } else {
+                        a = make_float2(x.x, -x.y);
+                        ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                        if (k == j + 1) s_alpha = a;
+                    }
+                }
+                vnew[k] = a;
+            }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_part[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) tot += s_part[w];
+        float tau = 0.f;
+        {
+            float ej = 0.f;
+            float2 v0 = s_alpha;
+            if (tot > 1e-30f) {
+                const float xn = sqrtf(tot);
+                const float2 alpha = v0;
+                const float aa = sqrtf(alpha.x * alpha.x + alpha.y * alpha.y);
+                float2 p1 = make_float2(1.f, 0.f);
+                if (aa > 0.f) p1 = make_float2(alpha.x / aa, alpha.y / aa);
+                v0 = make_float2(alpha.x + p1.x * xn, alpha.y + p1.y * xn);
+                tau = 1.f / (xn * (xn + aa));
+                ej = xn;
+                phase = cmulf(phase, make_float2(-p1.x, -p1.y));  // sub-diagonal element is -p1 * xn
+            }
+            if (tid == 0) {
+                vnew[j + 1] = v0;
+                taus[j] = tau;
+                e[j] = ej;
+                ph[j + 1] = phase;
+            }
+        }
+        __syncthreads();
+        // the reflector replaces the (now dead) part of row j right of the diagonal
+        {
+            float2* row = M + (size_t)j * ld;
+            for (int k = j + 1 + tid; k < r; k += TD_THREADS) row[k] = vnew[k];
+        }
+        float2 kacc = make_float2(0.f, 0.f);  // this warp's part of v^H (A0 v) resp. v^H p (identical on all its lanes)
+        const bool upd = !resident && (P == NB);
+        if (resident) {
+            for (int i = j + 1 + warp; i < r; i += TD_WARPS) {
+                float2* row = T + (size_t)(i - j0) * ts - j0;
+                const float2 vi = vprev[i], wi = wv[i];
+                float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+                for (int k = j + 1 + lane; k < r; k += 32) {
+                    float2 t = row[k];
+                    const float2 wk = wv[k], vk = vprev[k];
+                    t.x -= vi.x * wk.x + vi.y * wk.y + wi.x * vk.x + wi.y * vk.y;
+                    t.y -= vi.y * wk.x - vi.x * wk.y + wi.y * vk.x - wi.x * vk.y;
+                    row[k] = t;
+                    if (i == j + 1) nrow[k] = t;
+                    cfma(acc, t, vnew[k]);
+                }
+                acc.x = tau * warp_sum(acc.x);
+                acc.y = tau * warp_sum(acc.y);
+                const float2 v = vnew[i];
+                kacc.x += v.x * acc.x + v.y * acc.y;
+                kacc.y += v.x * acc.y - v.y * acc.x;
+                if (lane == 0) pv[i] = acc;
+            }
+        } else {
+            if (!upd && warp < P) {
+                // alpha_s = w_s^H v, beta_s = v_s^H v for the pending pair s = warp
+                float2 aa = make_float2(0.f, 0.f), bb = make_float2(0.f, 0.f);
+                for (int k = j + 1 + lane; k < r; k += 32) {
+                    const float2 v = vnew[k], wk = Wp[warp * WD + k], vk = Vp[warp * WD + k];
+                    aa.x = fmaf(wk.x, v.x, fmaf(wk.y, v.y, aa.x));
+                    aa.y = fmaf(wk.x, v.y, fmaf(-wk.y, v.x, aa.y));
+                    bb.x = fmaf(vk.x, v.x, fmaf(vk.y, v.y, bb.x));
+                    bb.y = fmaf(vk.x, v.y, fmaf(-vk.y, v.x, bb.y));
+                }
+                aa.x = warp_sum(aa.x), aa.y = warp_sum(aa.y), bb.x = warp_sum(bb.x), bb.y = warp_sum(bb.y);
+                if (lane == 0) s_ab[warp] = aa, s_ab[NB + warp] = bb;
+            }
+            // the reflector's entries for this lane's columns stay in registers for the whole pass
+            float2 vn[EPL];
+#pragma unroll
+            for (int ee = 0; ee < EPL; ++ee) {
+                const int k = ee * 32 + lane;
+                vn[ee] = (k > j && k < r) ? vnew[k] : make_float2(0.f, 0.f);
+            }
+            for (int ib = j + 1 + warp; ib < r; ib += TD_WARPS * RB) {
+                float2 x[RB][EPL];
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int i = ib + q * TD_WARPS;
+                    const float2* row = M + (size_t)i * ld;
+#pragma unroll
+                    for (int ee = 0; ee < EPL; ++ee) {
+                        const int k = ee * 32 + lane;
+                        x[q][ee] = (ee >= e0 && k > j && k < r && i < r) ? row[k] : make_float2(0.f, 0.f);
+                    }
+                }
+                if (upd) {
+#pragma unroll 1
+                    for (int s2 = 0; s2 < NB; ++s2) {
+                        float2 vi[RB], wi[RB];
+#pragma unroll
+                        for (int q = 0; q < RB; ++q) {
+                            const int i = ib + q * TD_WARPS;
+                            vi[q] = i < r ? Vp[s2 * WD + i] : make_float2(0.f, 0.f);
+                            wi[q] = i < r ? Wp[s2 * WD + i] : make_float2(0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int ee = 0; ee < EPL; ++ee) {
+                            if (ee >= e0) {
+                                const int k = ee * 32 + lane;
+                                const float2 wk = Wp[s2 * WD + k], vk = Vp[s2 * WD + k];
+#pragma unroll
+                                for (int q = 0; q < RB; ++q) {
+                                    x[q][ee].x -= vi[q].x * wk.x + vi[q].y * wk.y + wi[q].x * vk.x + wi[q].y * vk.y;
+                                    x[q][ee].y -= vi[q].y * wk.x - vi[q].x * wk.y + wi[q].y * vk.x - wi[q].x * vk.y;
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int i = ib + q * TD_WARPS;
+                    if (i < r) {
+                        float2* row = M + (size_t)i * ld;
+                        if (upd) {
+#pragma unroll
+                            for (int ee = 0; ee < EPL; ++ee) {
+                                const int k = ee * 32 + lane;
+                                if (ee >= e0 && k > j && k < r) row[k] = x[q][ee];
+                            }
+                        }
+                        if (i == j + 1) {
+#pragma unroll
+                            for (int ee = 0; ee < EPL; ++ee) {
+                                const int k = ee * 32 + lane;
+                                if (ee >= e0 && k > j && k < r) nrow[k] = x[q][ee];
+                            }
+                        }
+                        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int ee = 0; ee < EPL; ++ee)
+                            if (ee >= e0) cfma(acc, x[q][ee], vn[ee]);   // vn is zero at and left of column j
+                        const float ax = warp_sum(acc.x), ay = warp_sum(acc.y);
+                        const float2 v = vnew[i];
+                        kacc.x += v.x * ax + v.y * ay;
+                        kacc.y += v.x * ay - v.y * ax;
+                        if (lane == 0) pv[i] = make_float2(ax, ay);   // unscaled, uncorrected
+                    }
+                }
+            }
+        }
+        if (lane == 0) s_kpart[warp] = kacc;
+        __syncthreads();
+        float2 kk = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < TD_WARPS; ++w) kk.x += s_kpart[w].x, kk.y += s_kpart[w].y;
+        if (resident) {
+            // K = tau/2 * v^H p ;  w = p - K v
+            const float2 K = make_float2(0.5f * tau * kk.x, 0.5f * tau * kk.y);
+            for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
+                const float2 v = vnew[k], p = pv[k];
+                wv[k] = make_float2(p.x - (K.x * v.x - K.y * v.y), p.y - (K.x * v.y + K.y * v.x));
+            }
+            float2* t = vprev;
+            vprev = vnew;
+            vnew = t;
+        } else {
+            // p = tau (A0 v - sum_s [v_s alpha_s + w_s beta_s]) ; v^H p = tau (v^H A0 v - 2 Re sum_s conj(beta_s) alpha_s)
+            const int np = upd ? 0 : P;
+            for (int s2 = 0; s2 < np; ++s2) {
+                const float2 al = s_ab[s2], be = s_ab[NB + s2];
+                kk.x -= 2.f * (be.x * al.x + be.y * al.y);
+            }
+            const float2 K = make_float2(0.5f * tau * tau * kk.x, 0.5f * tau * tau * kk.y);
+            const int slot = upd ? 0 : P;
+            for (int k = j + 1 + tid; k < r; k += TD_THREADS) {
+                float2 p = pv[k];
+                for (int s2 = 0; s2 < np; ++s2) {
+                    const float2 al = s_ab[s2], be = s_ab[NB + s2];
+                    const float2 vk = Vp[s2 * WD + k], wk = Wp[s2 * WD + k];
+                    p.x -= vk.x * al.x - vk.y * al.y + wk.x * be.x - wk.y * be.y;
+                    p.y -= vk.x * al.y + vk.y * al.x + wk.x * be.y + wk.y * be.x;
+                }
+                const float2 v = vnew[k];
+                Wp[slot * WD + k] = make_float2(tau * p.x - (K.x * v.x - K.y * v.y), tau * p.y - (K.x * v.y + K.y * v.x));
+                Vp[slot * WD + k] = v;
+            }
+            P = upd ? 1 : P + 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (r == 1) {
+            d[0] = M[0].x;
+        } else {
+            const int j = r - 2;
+            float2 x00, x01, x11;
+            if (j0 >= 0) {
+                x00 = T[(size_t)(j - j0) * ts + j - j0], x01 = T[(size_t)(j - j0) * ts + j + 1 - j0];
+                x11 = T[(size_t)(j + 1 - j0) * ts + j + 1 - j0];
+            } else {
+                x00 = M[(size_t)j * ld + j], x01 = M[(size_t)j * ld + j + 1], x11 = M[(size_t)(j + 1) * ld + j + 1];
+            }
+            if (r >= 3) {
+                if (j0 >= 0) {
+                    const float2 v0 = vprev[j], v1 = vprev[j + 1], w0 = wv[j], w1 = wv[j + 1];
+                    x00.x -= 2.f * (v0.x * w0.x + v0.y * w0.y);
+                    x11.x -= 2.f * (v1.x * w1.x + v1.y * w1.y);
+                    x01.x -= v0.x * w1.x + v0.y * w1.y + w0.x * v1.x + w0.y * v1.y;
+                    x01.y -= v0.y * w1.x - v0.x * w1.y + w0.y * v1.x - w0.x * v1.y;
+                } else {
+                    for (int s2 = 0; s2 < P; ++s2) {
+                        const float2 v0 = Vp[s2 * WD + j], v1 = Vp[s2 * WD + j + 1], w0 = Wp[s2 * WD + j], w1 = Wp[s2 * WD + j + 1];
+                        x00.x -= 2.f * (v0.x * w0.x + v0.y * w0.y);
+                        x11.x -= 2.f * (v1.x * w1.x + v1.y * w1.y);
+                        x01.x -= v0.x * w1.x + v0.y * w1.y + w0.x * v1.x + w0.y * v1.y;
+                        x01.y -= v0.y * w1.x - v0.x * w1.y + w0.y * v1.x - w0.x * v1.y;
+                    }
+                }
+            }
+            d[j] = x00.x;
+            d[j + 1] = x11.x;
+            const float ea = sqrtf(x01.x * x01.x + x01.y * x01.y);  // sub-diagonal element is conj(x01)
+            e[j] = ea;
+            if (ea > 0.f) phase = cmulf(phase, make_float2(x01.x / ea, -x01.y / ea));
+            ph[j + 1] = phase;
+            taus[j] = 0.f;
+        }
+        e[r - 1] = 0.f;
+        taus[r - 1] = 0.f;
+    }
+}
+
 // ---- 2. Xt0 = (Q D)^T: row i = H_0 ... H_{r-3} e_i, kept in the registers of one warp for all reflectors -------------
 template <int EPL, int RPW>
 __global__ void __launch_bounds__(FQ_THREADS, (EPL <= 16) ? 2 : 1)
@@ -1504,6 +1828,21 @@ int launch_tridiag_sym(vk_context* h, cudaStream_t st, float2* W, int B, int r, 
     return VK_OK;
 }
 
+
+template <int EPL, int RB, int NB>
+int launch_tridiag_defer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
+                         float* tau, float2* ph) {
+    const size_t vec = (size_t)(5 + 2 * NB) * EPL * 32 * sizeof(float2);
+    int nts = (int)sqrt((double)(VK_SMEM_BUDGET - vec) / sizeof(float2));
+    if (nts > r) nts = r;
+    if (r > 384) nts = 0;  // see launch_tridiag
+    const size_t smem = vec + (size_t)nts * nts * sizeof(float2);
+    VK_CUDA(h, cudaFuncSetAttribute(tridiag_defer_kernel<EPL, RB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tridiag_defer_kernel<EPL, RB, NB><<<B, TD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
+}
+
 template <int EPL, int RPW>
 int launch_formq(vk_context* h, cudaStream_t st, const float2* W, int B, int r, int ld, size_t wstride, const float* tau,
                  const float2* ph, float2* X, const int32_t* skip) {
@@ -1583,7 +1922,13 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     if (dbg) cudaEventRecord(ev[0], st);
     // lower-triangle variant where it wins: 256 < r <= 512 (32.0 vs 35.3 ms per 296 matrices at r = 512; at r <= 256 the
     // full-storage kernel is faster, 1.98 vs 2.07 ms for 112 matrices of r = 256, above 512 it would spill)
-    if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    // deferred updates (kernel 1d): 29.4 vs 30.7 ms per 256 matrices of r = 512 against the lower-triangle kernel; at r = 256
+    // it is slower than kernel 1 (2.11 vs 1.98 ms per 112 matrices: both are bound by instruction issue - ncu: 1.0e9 warp
+    // instructions, issue slots 54 % busy with 4 warps per scheduler, FMA pipe 25 % - not by the bytes they move), so it is
+    // only taken there on request ("tridiag_impl" = 2)
+    if (r > 128 && r <= 256 && h->tridiag_impl == 2) rc = launch_tridiag_defer<8, 4, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r > 384 && r <= 512 && h->tridiag_impl != 1) rc = launch_tridiag_defer<16, 2, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 128) rc = launch_tridiag<4, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 256) rc = launch_tridiag<8, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);

@@ -120,19 +120,25 @@ def leaf_planes(zarr_path: str, ncorr: int) -> dict:
     return planes
 
 
-def construct_main_ds(zarr_path: str, column: str, batch_size: int):
+def construct_main_ds(zarr_path: str, column: str, batch_size: int, ngpus: int = 1):
     """Rebuild the visibility column from the leaf tree (reference construct_main_ds, decompress_ms.py:134-234).
 
     Device pipeline: per batch the zero-padded factors go to the GPU, vk_reconstruct_batched forms the matrices and
     vk_scatter_baselines writes them straight into the (row, chan, corr) column held on the device (including the
     unstacking of "diagonals" / "offdiagonals" leaves); the column comes back to the host once at the end.
+    ngpus > 1 (additive keyword): the reconstruction tasks are split into one contiguous range per GPU, one host thread
+    and handle each; every GPU scatters into its own zero-initialised copy of the column and the copies - disjoint by
+    construction - are summed on the host.
     Returns a visco_b200.msdata.VisData whose `data` is the reconstructed [row, chan, corr] complex64 array."""
     import os
+    import threading
 
     import torch
 
     from . import LOG
+    from .engine import Engine
     from .msdata import VisData
+    from .shard import shard_baselines
     from .zarr_leaf import list_subtables, read_svd_from_zarr
     eng = get_engine()
     dev = f"cuda:{eng.device}"
@@ -159,34 +165,62 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
         shape = [len(ant1), nchan, 4]
     ncorr = int(shape[2])
     planes = leaf_planes(zarr_path, ncorr)
-    out_dev = torch.zeros(tuple(int(x) for x in shape), dtype=torch.complex64, device=dev)
     batch_size = max(1, int(batch_size))
-    for start in range(0, len(tasks), batch_size):
-        batch = tasks[start:start + batch_size]
-        groups = {}
-        for t in batch:
-            if t[4] not in planes:
-                raise ValueError(f"unknown leaf name {t[4]}")
-            if any(p < 0 or p >= ncorr for p in planes[t[4]]):
-                # the reference's numpy assignment raises IndexError here (decompress_ms.py:222-229 on a 2-correlation column)
-                raise ValueError(f"leaf {t[4]} maps to correlation plane(s) {planes[t[4]]} but the column has {ncorr}")
-            stack = len(planes[t[4]])
-            if t[0].shape[0] != stack * t[3].size:
-                raise ValueError(f"leaf {t[4]} has {t[0].shape[0]} rows, the table has {t[3].size} for this baseline")
-            groups.setdefault((t[3].size, t[2].shape[1], stack), []).append(t)
-        for (m, n, stack), ts in groups.items():
-            B = len(ts)
-            kmax = max(1, max(t[1].shape[0] for t in ts))
-            U = np.zeros((B, stack * m, kmax), np.complex64)
-            S = np.zeros((B, kmax), np.float32)
-            Vt = np.zeros((B, kmax, n), np.complex64)
-            for b, t in enumerate(ts):
-                k = t[1].shape[0]
-                U[b, :, :k], S[b, :k], Vt[b, :k, :] = t[0], t[1], t[2]
-            rec = eng.reconstruct(torch.from_numpy(U).to(dev), torch.from_numpy(S).to(dev), torch.from_numpy(Vt).to(dev))
-            row_idx = torch.from_numpy(np.stack([t[3] for t in ts]).astype(np.int32)).to(dev)
-            corr_sel = torch.tensor([list(planes[t[4]]) for t in ts], dtype=torch.int32, device=dev)
-            eng.scatter_baselines(rec, out_dev, row_idx, corr_sel, stack)
+    for t in tasks:
+        if t[4] not in planes:
+            raise ValueError(f"unknown leaf name {t[4]}")
+        if any(p < 0 or p >= ncorr for p in planes[t[4]]):
+            # the reference's numpy assignment raises IndexError here (decompress_ms.py:222-229 on a 2-correlation column)
+            raise ValueError(f"leaf {t[4]} maps to correlation plane(s) {planes[t[4]]} but the column has {ncorr}")
+        if t[0].shape[0] != len(planes[t[4]]) * t[3].size:
+            raise ValueError(f"leaf {t[4]} has {t[0].shape[0]} rows, the table has {t[3].size} for this baseline")
+
+    def run(eng_g, my_tasks):
+        dev_g = f"cuda:{eng_g.device}"
+        with torch.cuda.device(eng_g.device):
+            out_g = torch.zeros(tuple(int(x) for x in shape), dtype=torch.complex64, device=dev_g)
+            for start in range(0, len(my_tasks), batch_size):
+                groups = {}
+                for t in my_tasks[start:start + batch_size]:
+                    groups.setdefault((t[3].size, t[2].shape[1], len(planes[t[4]])), []).append(t)
+                for (m, n, stack), ts in groups.items():
+                    B = len(ts)
+                    kmax = max(1, max(t[1].shape[0] for t in ts))
+                    U = np.zeros((B, stack * m, kmax), np.complex64)
+                    S = np.zeros((B, kmax), np.float32)
+                    Vt = np.zeros((B, kmax, n), np.complex64)
+                    for b, t in enumerate(ts):
+                        k = t[1].shape[0]
+                        U[b, :, :k], S[b, :k], Vt[b, :k, :] = t[0], t[1], t[2]
+                    rec = eng_g.reconstruct(torch.from_numpy(U).to(dev_g), torch.from_numpy(S).to(dev_g), torch.from_numpy(Vt).to(dev_g))
+                    row_idx = torch.from_numpy(np.stack([t[3] for t in ts]).astype(np.int32)).to(dev_g)
+                    corr_sel = torch.tensor([list(planes[t[4]]) for t in ts], dtype=torch.int32, device=dev_g)
+                    eng_g.scatter_baselines(rec, out_g, row_idx, corr_sel, stack)
+            return out_g
+
+    ngpus = max(1, min(int(ngpus or 1), torch.cuda.device_count(), max(1, len(tasks))))
+    if ngpus == 1:
+        out_dev = run(eng, tasks)
+    else:
+        parts, errors = [None] * ngpus, []
+
+        def worker(g):
+            try:
+                off, cnt = shard_baselines(len(tasks), ngpus, g)
+                e_g = eng if g == eng.device else Engine(g)
+                parts[g] = run(e_g, tasks[off:off + cnt]).cpu()
+            except BaseException as ex:
+                errors.append(ex)
+        threads = [threading.Thread(target=worker, args=(g,)) for g in range(ngpus)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        out_dev = parts[0]
+        for p_ in parts[1:]:
+            out_dev += p_
     out = out_dev.cpu().numpy()
     # flags: unpack the bit-packed FLAGS / FLAGS_ROW groups (reference :240-246)
     flag = flag_row = None
@@ -214,16 +248,16 @@ def construct_main_ds(zarr_path: str, column: str, batch_size: int):
                    flag=flag, flag_row=flag_row, weight_spectrum=weights, sigma_spectrum=weights)
 
 
-def open_dataset(zarr_path: str, column: str = "COMPRESSED_DATA", batch_size: int = 50):
+def open_dataset(zarr_path: str, column: str = "COMPRESSED_DATA", batch_size: int = 50, ngpus: int = 1):
     """Decompress to an in-memory data set without writing an MS (reference open_dataset, decompress_ms.py:295-326)."""
-    return construct_main_ds(zarr_path, column, batch_size)
+    return construct_main_ds(zarr_path, column, batch_size, ngpus=ngpus)
 
 
-def write_datasets_to_ms(zarr_path: str, msname: str, column: str, batch_size: int):
+def write_datasets_to_ms(zarr_path: str, msname: str, column: str, batch_size: int, ngpus: int = 1):
     """Decompress a store into `msname` (reference write_datasets_to_ms, decompress_ms.py:329-402). Writing a casacore
     Measurement Set needs dask-ms / python-casacore (out of scope, absent here): an ``.npz`` bundle name is written
     directly, anything else raises unless python-casacore is importable."""
-    vis = construct_main_ds(zarr_path, column, batch_size)
+    vis = construct_main_ds(zarr_path, column, batch_size, ngpus=ngpus)
     if str(msname).endswith(".npz"):
         vis.save(msname)
         return msname

@@ -35,6 +35,9 @@ class Engine:
             raise RuntimeError(f"vk_create failed with status {rc} (is this an sm_100 GPU?)")
         self.h = h
         self._lock = threading.Lock()
+        # stream of the host-buffer entry points: None = the legacy default stream; a torch.cuda.Stream lets several
+        # engines (one per host thread) overlap their copies and kernels on one GPU
+        self.host_stream = None
 
     # ------------------------------------------------------------------------------------------ plumbing
     def close(self):
@@ -293,7 +296,7 @@ class Engine:
             assert U.shape == (B, m, kmax) and S.shape == (B, kmax) and Vt.shape == (B, kmax, n)
             assert all(x.flags.c_contiguous for x in out)
         with self._lock:
-            self.lib.vk_set_stream(self.h, C.c_void_p(0))
+            self.lib.vk_set_stream(self.h, C.c_void_p(self.host_stream.cuda_stream if self.host_stream is not None else 0))
             rc = self.lib.vk_compress_host(self.h, A.ctypes.data, B, m, n, int(compressionrank or 0),
                                            float(decorrelation or 0.0), kmax, U.ctypes.data, S.ctypes.data,
                                            Vt.ctypes.data, ranks.ctypes.data, stats.ctypes.data)
@@ -315,7 +318,7 @@ class Engine:
         if ranks is not None:
             rp = np.ascontiguousarray(ranks, dtype=np.int32)
         with self._lock:
-            self.lib.vk_set_stream(self.h, C.c_void_p(0))
+            self.lib.vk_set_stream(self.h, C.c_void_p(self.host_stream.cuda_stream if self.host_stream is not None else 0))
             rc = self.lib.vk_reconstruct_host(self.h, U.ctypes.data, S.ctypes.data, Vt.ctypes.data,
                                               rp.ctypes.data if rp is not None else None, B, m, n, kmax,
                                               out.ctypes.data)

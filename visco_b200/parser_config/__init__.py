@@ -29,13 +29,15 @@ COMPRESS_OPTIONS = [
     ("column", "col", str, "DATA", False, "Column to compress."),
     ("outcolumn", "oc", str, "COMPRESSED_DATA", False, "Name of the compressed column in the store."),
     ("batch_size", "bs", int, 20, False, "Baselines per batch."),
-    ("use_model_data", "umd", bool, None, False, "Replace flagged data with model data (not implemented)."),
+    ("use_model_data", "umd", bool, None, False, "Replace flagged data with model data."),
     ("model_data", "md", str, None, False, "Model data column."),
-    ("flagestimate", "fest", bool, None, False, "Estimate flagged values (not implemented)."),
-    ("flagvalue", "fv", str, None, False, "Constant for flagged values (not implemented)."),
+    ("flagestimate", "fest", bool, None, False, "Estimate flagged values with scipy griddata (out of scope of this build: raises)."),
+    ("flagvalue", "fv", str, None, False, "Constant that replaces flagged values, e.g. 0 or 1+1j."),
     ("decorrelation", "dec", float, None, False, "Keep singular values up to this decorrelation (energy = dec^2)."),
     ("compressionrank", "cr", int, None, False, "Keep this many singular values (wins over --decorrelation)."),
     ("antennas", None, str, None, False, "List of antenna indices, e.g. '[0,1,2]'."),
+    # additive (not in the reference): GPUs of this box to spread the baselines over
+    ("ngpus", "ng", int, 1, False, "GPUs to shard the baselines over (one host thread and handle per GPU)."),
 ]
 # reference visco/parser_config/decompressms.yaml:2-26
 DECOMPRESS_OPTIONS = [
@@ -43,6 +45,7 @@ DECOMPRESS_OPTIONS = [
     ("ms", "ms", str, "decompressed.ms", False, "The output Measurement Set."),
     ("column", "col", str, "COMPRESSED_DATA", False, "Compressed column to decompress."),
     ("batch_size", "bs", int, 50, False, "Reconstruction tasks per batch."),
+    ("ngpus", "ng", int, 1, False, "GPUs to shard the reconstruction tasks over (additive option)."),
 ]
 
 
@@ -90,7 +93,7 @@ def compressrunit(**kw):
         ddid=kw["ddid"], scan=kw["scan"], column=kw["column"], outcolumn=kw["outcolumn"], batch_size=kw["batch_size"],
         dashboard_addr=kw["dashboard_address"], host_addr=kw["host_address"], use_model_data=bool(kw["use_model_data"]),
         model_data=kw["model_data"], flag_estimate=bool(kw["flagestimate"]), decorrelation=kw["decorrelation"],
-        compressionrank=kw["compressionrank"], flagvalue=kw["flagvalue"], antennas=antennas)
+        compressionrank=kw["compressionrank"], flagvalue=kw["flagvalue"], antennas=antennas, ngpus=kw["ngpus"])
 
 
 @cli.command("decompressms")
@@ -99,7 +102,7 @@ def compressrunit(**kw):
 def decompressrunit(**kw):
     """Decompress a store back to a Measurement Set (reference parser_config/decompressms.py:23-33)."""
     from visco_b200 import decompress_ms
-    decompress_ms.write_datasets_to_ms(kw["zarrstore"], kw["ms"], kw["column"], kw["batch_size"])
+    decompress_ms.write_datasets_to_ms(kw["zarrstore"], kw["ms"], kw["column"], kw["batch_size"], ngpus=kw["ngpus"])
 
 
 def main():
