@@ -1925,7 +1925,9 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     // deferred updates (kernel 1d): 29.4 vs 30.7 ms per 256 matrices of r = 512 against the lower-triangle kernel; at r = 256
     // it is slower than kernel 1 (2.11 vs 1.98 ms per 112 matrices: both are bound by instruction issue - ncu: 1.0e9 warp
     // instructions, issue slots 54 % busy with 4 warps per scheduler, FMA pipe 25 % - not by the bytes they move), so it is
-    // only taken there on request ("tridiag_impl" = 2)
+    // only taken there on request ("tridiag_impl" = 2). Also measured and dropped at r = 256: the same kernel with packed
+    // fma.rn.f32x2 arithmetic and (x, x, y, y) operand vectors (6 packed FMAs per element instead of 12 scalar ones, two rows
+    // per warp to stay inside 128 registers): 2.09 ms
     if (r > 128 && r <= 256 && h->tridiag_impl == 2) rc = launch_tridiag_defer<8, 4, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 384 && r <= 512 && h->tridiag_impl != 1) rc = launch_tridiag_defer<16, 2, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
