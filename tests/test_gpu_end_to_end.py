@@ -198,3 +198,57 @@ def test_weight_spectrum_rank1_and_the_reference_decompression_quirk(tmp_path):
     assert out.weight_spectrum.shape == (nrow, 1, ncorr)
     np.testing.assert_allclose(out.weight_spectrum, ref, rtol=1e-4, atol=1e-6)
     assert out.sigma_spectrum is out.weight_spectrum or np.array_equal(out.sigma_spectrum, out.weight_spectrum)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The sample Measurement Set itself through the command line (reference tests/compression_tests.py:5-32,
+# decompression_tests.py:10-12): every one of its 21 baselines, read by visco_b200.casatable (no python-casacore here).
+# ---------------------------------------------------------------------------------------------------------------------
+SAMPLE_MS = os.path.join(ROOT, "tests", "golden", "sim-visco-kat7-subset.ms")
+
+
+def test_cli_compresses_the_sample_measurement_set(tmp_path):
+    from click.testing import CliRunner
+    from visco_b200.decompress_ms import open_dataset
+    from visco_b200.parser_config import cli
+    from visco_b200.zarr_leaf import list_subtables
+    z = str(tmp_path / "sim-visco-kat7.zarr")
+    r = CliRunner().invoke(cli, ["compressms", "-ms", SAMPLE_MS, "-zs", z, "-corr", "XX,YY", "-dec", "0.90", "-bs", "10",
+                                 "-l", "3", "-nw", "1", "-nt", "1"], catch_exceptions=False)
+    assert r.exit_code == 0, r.output
+    base = os.path.join(z, "MAIN", "COMPRESSED_DATA")
+    assert len(list_subtables(base)) == 21 and list_subtables(os.path.join(base, "ANT-2&ANT-5")) == ["XX", "YY"]
+    assert os.path.exists(os.path.join(z, ".zmetadata"))
+    vis = VisData.load(SAMPLE_MS)
+    back = open_dataset(z)
+    ref = _oracle_decompressed(vis, "XX,YY", False, decorrelation=0.90)
+    for c in (0, 3):
+        num = np.linalg.norm(back.data[:, :, c] - ref[:, :, c])
+        assert num <= 2e-4 * np.linalg.norm(ref[:, :, c]), c       # same ranks, same projections as the reference's path
+    assert not back.data[:, :, 1:3].any() and back.flag.shape == vis.data.shape and not back.flag.any()
+    out = str(tmp_path / "decompressed.npz")
+    r = CliRunner().invoke(cli, ["decompressms", "-zs", z, "-ms", out], catch_exceptions=False)
+    assert r.exit_code == 0 and VisData.load(out).data.shape == vis.data.shape
+
+
+def test_sharded_drivers_match_the_single_gpu_result(tmp_path):
+    """--ngpus: baselines / reconstruction tasks split over the GPUs of the box, one host thread and handle each
+    (the role of the reference's nworkers, compress_ms.py:571-697). Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from visco_b200.compress_ms import compress_full_ms
+    from visco_b200.decompress_ms import open_dataset
+    from visco_b200.zarr_leaf import list_subtables, read_svd_from_zarr
+    z1, z2 = str(tmp_path / "one.zarr"), str(tmp_path / "two.zarr")
+    kw = dict(KW, correlation="XX,YY", compressionrank=3)
+    assert compress_full_ms(ms_path=SAMPLE_MS, zarr_path=z1, **kw) == 21
+    assert compress_full_ms(ms_path=SAMPLE_MS, zarr_path=z2, ngpus=2, **kw) == 21
+    b1, b2 = (os.path.join(z, "MAIN", "COMPRESSED_DATA") for z in (z1, z2))
+    assert list_subtables(b1) == list_subtables(b2)
+    for bl in list_subtables(b1):
+        for c in ("XX", "YY"):
+            f1, f2 = read_svd_from_zarr(os.path.join(b1, bl, c)), read_svd_from_zarr(os.path.join(b2, bl, c))
+            np.testing.assert_array_equal(f1[1], f2[1])              # same kernels, same inputs: identical singular values
+    d1, d2 = open_dataset(z1), open_dataset(z2, ngpus=2)
+    np.testing.assert_array_equal(d1.data, d2.data)

@@ -86,6 +86,20 @@ class VisData:
                 raise ValueError(f"Measurement Set bundle {path} does not exist")
             with np.load(path, allow_pickle=False) as z:
                 key = column if column in z.files else "DATA"
+                keep = None
+                for col, val in (("SCAN_NUMBER", scan), ("FIELD_ID", fieldid), ("DATA_DESC_ID", ddid)):
+                    if col in z.files and val is not None:
+                        ok = z[col] == int(val)
+                        if not ok.any():
+                            raise ValueError(f"Invalid selected {col} {val}. Available: {np.unique(z[col]).tolist()}")   # reference :461-468
+                        keep = ok if keep is None else (keep & ok)
+                if keep is not None and not keep.all():
+                    def rows(name):
+                        return z[name][keep] if name in z.files else None
+                    return cls(data=z[key][keep], antenna1=z["ANTENNA1"][keep], antenna2=z["ANTENNA2"][keep],
+                               antenna_names=list(z["ANTENNA_NAME"]), corr_types=list(z["CORR_TYPE"]), rowid=z["ROWID"][keep],
+                               flag=rows("FLAG"), flag_row=rows("FLAG_ROW"), model_data=rows("MODEL_DATA"),
+                               weight_spectrum=rows("WEIGHT_SPECTRUM"), column=column)
                 return cls(data=z[key], antenna1=z["ANTENNA1"], antenna2=z["ANTENNA2"],
                            antenna_names=list(z["ANTENNA_NAME"]), corr_types=list(z["CORR_TYPE"]), rowid=z["ROWID"],
                            flag=z["FLAG"] if "FLAG" in z.files else None,
@@ -96,10 +110,8 @@ class VisData:
             raise ValueError(f"Measurement Set {path} does not exist")     # reference compress_ms.py:876-877
         try:
             from casacore.tables import table  # type: ignore
-        except ImportError as e:
-            raise RuntimeError(
-                "reading a casacore Measurement Set needs python-casacore, which is not installed in this environment; "
-                "convert the MS columns to an .npz bundle (visco_b200.msdata.VisData.save) or install python-casacore") from e
+        except ImportError:
+            return cls._load_without_casacore(path, column, scan, fieldid, ddid)
         t = table(path, ack=False)
         q = []
         if scan is not None:
@@ -114,9 +126,35 @@ class VisData:
                 raise ValueError("Invalid selection: no rows match scan/field/ddid")    # reference :461-468
         names = list(table(os.path.join(path, "ANTENNA"), ack=False).getcol("NAME"))
         corr = list(table(os.path.join(path, "POLARIZATION"), ack=False).getcol("CORR_TYPE")[0])
+        have = set(t.colnames())
+        # ROWID as dask-ms defines it: the row number in the parent table (what the leaves store as `time`)
         return cls(data=t.getcol(column), antenna1=t.getcol("ANTENNA1"), antenna2=t.getcol("ANTENNA2"), antenna_names=names,
                    corr_types=corr, rowid=np.asarray(t.rownumbers(), dtype=np.int64), column=column,
-                   weight_spectrum=t.getcol("WEIGHT_SPECTRUM") if "WEIGHT_SPECTRUM" in t.colnames() else None)
+                   flag=t.getcol("FLAG") if "FLAG" in have else None,
+                   flag_row=t.getcol("FLAG_ROW") if "FLAG_ROW" in have else None,
+                   model_data=t.getcol("MODEL_DATA") if ("MODEL_DATA" in have and column != "MODEL_DATA") else None,
+                   weight_spectrum=t.getcol("WEIGHT_SPECTRUM") if "WEIGHT_SPECTRUM" in have else None)
+
+    @classmethod
+    def _load_without_casacore(cls, path, column, scan, fieldid, ddid):
+        """Measurement Set through visco_b200.casatable (tiled + StandardStMan columns only). The selection columns
+        (SCAN_NUMBER / FIELD_ID / DATA_DESC_ID) and FLAG_ROW sit in an IncrementalStMan in such files and are not
+        decoded: the whole table is taken, with a warning when a selection was asked for."""
+        from . import LOG
+        from .casatable import CasaTableError, read_measurement_set
+        try:
+            ms = read_measurement_set(path, column)
+        except (CasaTableError, OSError, KeyError, ValueError) as e:
+            raise RuntimeError(
+                f"cannot read {path} without python-casacore ({e}); convert the MS columns to an .npz bundle "
+                "(visco_b200.msdata.VisData.save) or install python-casacore") from e
+        if any(v not in (None, 0, 1) for v in (scan, fieldid, ddid)):
+            LOG.warning("python-casacore is not installed: SCAN_NUMBER / FIELD_ID / DATA_DESC_ID cannot be read, the whole "
+                        "table is compressed as one scan / field / data description")
+        return cls(data=ms["data"], antenna1=ms["ANTENNA1"], antenna2=ms["ANTENNA2"], antenna_names=ms["names"],
+                   corr_types=ms["corr_types"], rowid=np.arange(ms["nrow"], dtype=np.int64), column=column,
+                   flag=ms.get("FLAG"), model_data=ms.get("MODEL_DATA") if column != "MODEL_DATA" else None,
+                   weight_spectrum=ms.get("WEIGHT_SPECTRUM"))
 
     # --------------------------------------------------------------------------------------------- hot-path helpers
     def baselines(self, antennas=None):
