@@ -18,8 +18,9 @@
 //     contraction is at most 32 long, i.e. at most 24 MMAs per accumulator chain, so no second accumulation level.
 //   * 8 converter/epilogue warps: load the raw Vt tile of tile t+1 into registers (plain coalesced 128-bit loads: 64 bytes
 //     per thread, no TMA needed at this size), split + store tile t's operand in the MN-major SWIZZLE_128B_BASE32B layout,
-//     then drain tile t-1 from TMEM and stream it to HBM while the tensor core works on tile t. Two operand buffers and
-//     two TMEM accumulator pairs (2 x 256 columns) carry the overlap; one elected thread issues the MMAs.
+//     then drain tile t-1 from TMEM into a per-warp staging block and hand it to the TMA unit (bulk tensor stores) while
+//     the tensor core works on tile t. Two operand buffers and two TMEM accumulator pairs (2 x 256 columns) carry the
+//     overlap; one elected thread issues the MMAs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -57,19 +58,35 @@ struct TileRef {
     int b, m0, n0c, t;
 };
 
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // Drain one finished tile: TMEM -> registers (one accumulator row per thread) -> complex values -> the warp's own 8 KiB
-// staging block in shared memory (32 rows x 256 bytes, 16-byte chunks XOR-swizzled with the row: conflict free both ways)
-// -> HBM as two 256-byte row segments per warp instruction (whole 32-byte sectors). Writing the rows straight from the
-// accumulator registers (16 bytes per lane, lanes 16 KiB apart) costs a memory transaction per lane and ran at 14 GB/s per
-// SM. No CTA-wide barrier: the eight warps drift freely.
-__device__ __forceinline__ void rt_epilogue(const ReconArgs& g, const TileRef& tr, uint32_t bar_accfull, uint32_t bar_accfree,
-                                            uint32_t tmem_base, unsigned char* stage, int quad, int chalf, int lane, int cwarp) {
+// staging block in shared memory (two TMA boxes of 32 rows x 128 bytes, SWIZZLE_128B: a lane writes its own row, the
+// 16-byte chunk index XOR-ed with the row keeps the 128-bit stores conflict free) -> HBM by two bulk tensor stores that one
+// lane issues: whole 128-byte lines, clipped by the tensor map at the ragged ends of m and n, and asynchronous - the warp
+// goes on to the next tile while the TMA unit reads the block; it only waits for that read before writing the block again.
+// (Earlier variants: rows stored straight from the accumulator registers, 16 bytes per lane and lanes a row apart - a
+// memory transaction per lane, 14 GB/s per SM; staged block read back and stored by the warp itself - 0.64 of HBM, the
+// eight warps were latency bound on the shared-memory round trip.) No CTA-wide barrier: the eight warps drift freely.
+__device__ __forceinline__ void rt_epilogue(const CUtensorMap* mapO, const TileRef& tr, uint32_t bar_accfull,
+                                            uint32_t bar_accfree, uint32_t tmem_base, uint32_t stage, int quad, int chalf,
+                                            int lane, int cwarp) {
     const int s = tr.t & 1;
     mbar_wait(bar_accfull + 8 * s, ((uint32_t)tr.t >> 1) & 1);
     fence_after_sync();
-    unsigned char* st = stage + cwarp * (32 * 256);   // this warp's rows quad*32 .. +31, complex columns chalf*32 .. +31
+    const uint32_t st = stage + cwarp * (32 * 256);   // this warp's rows quad*32 .. +31, complex columns chalf*32 .. +31
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 256 + chalf * 64);
-    __syncwarp();  // the previous tile has left the block
+    // the bulk stores of the previous tile must have read the block
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t d1a[16], d1b[16], d2a[16], d2b[16];
@@ -83,7 +100,8 @@ __device__ __forceinline__ void rt_epilogue(const ReconArgs& g, const TileRef& t
             fence_before_sync();
             mbar_arrive(bar_accfree + 8 * s);
         }
-        // 32 accumulator columns = 16 complex outputs = 8 chunks of 16 bytes: chunks h*8 + q of this thread's row
+        // 32 accumulator columns = 16 complex outputs = 8 chunks of 16 bytes = box h of this thread's row
+        const uint32_t rowaddr = st + h * 4096 + lane * 128;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const uint32_t* p1 = q < 4 ? d1a : d1b;
@@ -93,27 +111,20 @@ __device__ __forceinline__ void rt_epilogue(const ReconArgs& g, const TileRef& t
                                          __uint_as_float(p1[o + 1]) + __uint_as_float(p2[o]),
                                          __uint_as_float(p1[o + 2]) - __uint_as_float(p2[o + 3]),
                                          __uint_as_float(p1[o + 3]) + __uint_as_float(p2[o + 2]));
-            const int c = h * 8 + q;
-            *reinterpret_cast<float4*>(st + lane * 256 + ((c ^ (lane & 15)) << 4)) = r;
+            sts128(rowaddr + ((q ^ (lane & 7)) << 4), r);
         }
     }
-    __syncwarp();  // the block is staged
-    // lanes 0..15 write row rr, lanes 16..31 row rr + 1: 256 contiguous bytes each
-    const int c = lane & 15;
-    const int v = tr.n0c + chalf * 32 + 2 * c;
-#pragma unroll 4
-    for (int rr = lane >> 4; rr < 32; rr += 2) {
-        const int gi = tr.m0 + quad * 32 + rr;
-        const float4 r = *reinterpret_cast<const float4*>(st + rr * 256 + ((c ^ (rr & 15)) << 4));
-        if (gi < g.m) {
-            float2* orow = g.out + ((size_t)tr.b * g.m + gi) * g.n;
-            if (v + 1 < g.n) __stcs(reinterpret_cast<float4*>(orow + v), r);
-            else if (v < g.n) orow[v] = make_float2(r.x, r.y);
-        }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();  // the block is staged and visible to the async proxy
+    if (lane == 0) {
+        const int c0 = 2 * (tr.n0c + chalf * 32), c1 = tr.m0 + quad * 32;
+        tma_store_3d(mapO, st, c0, c1, tr.b);
+        tma_store_3d(mapO, st + 4096, c0 + 32, c1, tr.b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 }
 
-__global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const ReconArgs g) {
+__global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const __grid_constant__ CUtensorMap mapO, const ReconArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const ReconArgs
             load_raw(nt0);
             // the previous panel's last tile must have left the tensor core before its A operand is replaced
             if (pending) {
-                rt_epilogue(g, prev, bar_accfull, bar_accfree, tmem_base, smem + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
+                rt_epilogue(&mapO, prev, bar_accfull, bar_accfree, tmem_base, sbase + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
                 pending = false;
             }
             // ---- A operand of the panel: Pr = Re(U S), Pi = Im(U S), hi / lo, K-major SWIZZLE_128B ----
@@ -248,10 +259,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const ReconArgs
                     const Split4 sr = split4(make_float4(pr[0], pr[1], pr[2], pr[3]));
                     const Split4 si = split4(make_float4(pi[0], pi[1], pi[2], pi[3]));
                     const uint32_t off = (uint32_t)row * 128 + (uint32_t)((chunk ^ (row & 7)) << 4);
-                    *reinterpret_cast<float4*>(smem + RT_OFF_A + off) = sr.hi;
-                    *reinterpret_cast<float4*>(smem + RT_OFF_A + RT_A_BYTES + off) = sr.lo;
-                    *reinterpret_cast<float4*>(smem + RT_OFF_A + 2 * RT_A_BYTES + off) = si.hi;
-                    *reinterpret_cast<float4*>(smem + RT_OFF_A + 3 * RT_A_BYTES + off) = si.lo;
+                    sts128(sbase + RT_OFF_A + off, sr.hi);
+                    sts128(sbase + RT_OFF_A + RT_A_BYTES + off, sr.lo);
+                    sts128(sbase + RT_OFF_A + 2 * RT_A_BYTES + off, si.hi);
+                    sts128(sbase + RT_OFF_A + 3 * RT_A_BYTES + off, si.lo);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(bar_afull);
@@ -260,8 +271,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const ReconArgs
                 const int s = t & 1;
                 const uint32_t use = (uint32_t)t >> 1;
                 mbar_wait(bar_bfree + 8 * s, (use & 1) ^ 1);
-                unsigned char* b_hi = smem + RT_OFF_B + s * 2 * RT_B_BYTES;
-                unsigned char* b_lo = b_hi + RT_B_BYTES;
+                const uint32_t b_hi = sbase + RT_OFF_B + s * 2 * RT_B_BYTES;
+                const uint32_t b_lo = b_hi + RT_B_BYTES;
 #pragma unroll
                 for (int i = 0; i < RT_KMAX / 8; ++i) {
                     if (i < nq) {
@@ -271,19 +282,20 @@ __global__ void __launch_bounds__(RT_THREADS, 1) recon_tc_kernel(const ReconArgs
                         const Split4 sp = split4(raw[i]);
                         // MN-major SWIZZLE_128B_BASE32B: 32-byte chunk index (lc >> 1) XOR (row & 3); 16-byte halves keep order
                         const uint32_t o = (uint32_t)(grp * RT_KMAX + c) * 128 + (uint32_t)(((((lc >> 1) ^ (c & 3)) << 1) | (lc & 1)) << 4);
-                        *reinterpret_cast<float4*>(b_hi + o) = sp.hi;
-                        *reinterpret_cast<float4*>(b_lo + o) = sp.lo;
+                        sts128(b_hi + o, sp.hi);
+                        sts128(b_lo + o, sp.lo);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(bar_bfull + 8 * s);
                 if (nt + 1 < nt1) load_raw(nt + 1);
-                if (pending) rt_epilogue(g, prev, bar_accfull, bar_accfree, tmem_base, smem + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
+                if (pending) rt_epilogue(&mapO, prev, bar_accfull, bar_accfree, tmem_base, sbase + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
                 pending = true;
                 prev = {b, m0, nt * RT_NC, t};
             }
         }
-        if (pending) rt_epilogue(g, prev, bar_accfull, bar_accfree, tmem_base, smem + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
+        if (pending) rt_epilogue(&mapO, prev, bar_accfull, bar_accfree, tmem_base, sbase + RT_OFF_STAGE, quad, chalf, lane, warp - 4);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory outlives the bulk stores
     }
     fence_before_sync();
     __syncthreads();
@@ -313,7 +325,18 @@ int vk_launch_recon_tc_smallk(vk_context* h, const float2* U, const float* S, co
     if (panels * nsplit > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "reconstruct: too many tiles");
     g.items = (int)(panels * nsplit);
     const int grid = g.items < h->num_sms ? g.items : h->num_sms;
-    recon_tc_kernel<<<grid, RT_THREADS, RT_SMEM, h->stream>>>(g);
+    // output as a 3-D tensor (2n floats, m rows, B matrices): boxes of 32 rows x 128 bytes, clipped at m and 2n
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    CUtensorMap mapO;
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * n, (cuuint64_t)m, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)n * 8, (cuuint64_t)m * n * 8};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (reconstruction output) failed: " + std::to_string((int)r));
+    recon_tc_kernel<<<grid, RT_THREADS, RT_SMEM, h->stream>>>(mapO, g);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
