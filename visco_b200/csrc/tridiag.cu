@@ -1928,7 +1928,10 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     // only taken there on request ("tridiag_impl" = 2). Also measured and dropped at r = 256: the same kernel with packed
     // fma.rn.f32x2 arithmetic and (x, x, y, y) operand vectors (6 packed FMAs per element instead of 12 scalar ones, two rows
     // per warp to stay inside 128 registers): 2.09 ms
-    if (r > 128 && r <= 256 && h->tridiag_impl == 2) rc = launch_tridiag_defer<8, 4, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    // "tridiag_impl": 0 = lower triangle + deferred updates (tridiag_sym.cu) where it applies, 1 = the undeferred kernels,
+    // 2 = the full-storage deferred kernel 1d
+    if (h->tridiag_impl == 0 && vk_tridiag_symdefer_supported(r)) rc = vk_launch_tridiag_symdefer(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r > 128 && r <= 256 && h->tridiag_impl == 2) rc = launch_tridiag_defer<8, 4, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 384 && r <= 512 && h->tridiag_impl != 1) rc = launch_tridiag_defer<16, 2, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
