@@ -410,6 +410,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "tridiag_impl")
         h->tridiag_impl = (int)v;
+    else if (k == "tridiag_variant")
+        h->tridiag_variant = (int)v;
     else if (k == "eigvec_impl")
         h->eigvec_impl = (int)v;
     else if (k == "ql_maxit")

@@ -41,6 +41,7 @@ struct vk_context {
     int chunk = 0;  // matrices per internal pass, 0 = auto
     int topk = 0;            // 0 = auto (subspace iteration for compressionrank <= 4), 1 = full Jacobi only, 2 = up to rank 8
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
+    int tridiag_variant = 0;  // tridiag_sym.cu: 0 = by batch size, 1 = one matrix per SM, 2 = two per SM
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems

@@ -35,16 +35,14 @@
 
 namespace {
 
-constexpr int SD_THREADS = 512;
-constexpr int SD_WARPS = SD_THREADS / 32;
 
 __device__ __forceinline__ float2 cmulf2(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 // x -= vi conj(wk) + wi conj(vk)
 __device__ __forceinline__ void rank2(float2& x, float2 vi, float2 wi, float2 vk, float2 wk) {
-    x.x -= vi.x * wk.x + vi.y * wk.y + wi.x * vk.x + wi.y * vk.y;
-    x.y -= vi.y * wk.x - vi.x * wk.y + wi.y * vk.x - wi.x * vk.y;
+    x.x = fmaf(-vi.x, wk.x, fmaf(-vi.y, wk.y, fmaf(-wi.x, vk.x, fmaf(-wi.y, vk.y, x.x))));
+    x.y = fmaf(-vi.y, wk.x, fmaf(vi.x, wk.y, fmaf(-wi.y, vk.x, fmaf(wi.x, vk.y, x.y))));
 }
 // pending pair s at index i: (v.x, v.y, w.x, w.y)
 __device__ __forceinline__ void rank2p(float2& x, float4 a, float4 c) {
@@ -79,11 +77,14 @@ struct TileIt {
     bool valid;
 };
 
-template <int EPL, int TR, int NB, bool RAGGED>
-__global__ void __launch_bounds__(SD_THREADS, 1)
+// NT threads per CTA (512: one CTA per SM, the whole SM on one matrix - few matrices; 256: two CTAs, i.e. two matrices, per
+// SM so that one's barriers and scalar phases hide behind the other's pass - many matrices); DB: register double buffer
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED>
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     tridiag_symdefer_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
                             float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
     constexpr int WD = EPL * 32;
+    constexpr int SD_THREADS = NT, SD_WARPS = NT / 32;
     static_assert(NB <= SD_WARPS, "one warp per pending pair computes its two inner products");
     static_assert(TR == 8 || TR == 16, "row block height");
     extern __shared__ float2 sd_sm[];
@@ -267,15 +268,22 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
                     else x[rr] = src[(size_t)rr * ld];
                 }
             };
-            float2 racc[TR];
+            constexpr bool CACHE_V = TR == 8;            // (16 cached rows spill at 128 registers)
+            float2 racc[TR], vrow[CACHE_V ? TR : 1];     // row parts and v_i of the current block
 #pragma unroll
             for (int rr = 0; rr < TR; ++rr) racc[rr] = make_float2(0.f, 0.f);
+            int vblock = -1;
             auto process = [&](const TileIt& t, float2 (&x)[TR]) {
                 const int i0 = t.I * TR;
                 const int k = t.K * 32 + lane;
                 const bool last = t.K == t.Klast;
+                if (CACHE_V && t.I != vblock) {
+                    vblock = t.I;
+#pragma unroll
+                    for (int rr = 0; rr < TR; ++rr) vrow[rr] = vnew[i0 + rr];   // i0 + rr < WD; zero at and left of j, beyond r
+                }
                 if (upd) {
-#pragma unroll 2
+#pragma unroll 1
                     for (int s2 = 0; s2 < NB; ++s2) {
                         const float4 c = VW[s2 * WD + k];
 #pragma unroll
@@ -298,7 +306,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
                     }
 #pragma unroll
                     for (int rr = 0; rr < TR; ++rr) {
-                        const float2 vi = vnew[i0 + rr];
+                        const float2 vi = CACHE_V ? vrow[CACHE_V ? rr : 0] : vnew[i0 + rr];
                         cfma(racc[rr], x[rr], vk);
                         // strictly below the diagonal: (A v)_k += conj(a_ik) v_i
                         yk.x = fmaf(x[rr].x, vi.x, fmaf(x[rr].y, vi.y, yk.x));
@@ -309,10 +317,10 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
 #pragma unroll
                     for (int rr = 0; rr < TR; ++rr) {
                         const int i = i0 + rr;
-                        const float2 vi = vnew[i < WD ? i : WD - 1];
+                        const float2 vi = CACHE_V ? vrow[CACHE_V ? rr : 0] : vnew[i];
                         float2 xx = k <= i ? x[rr] : make_float2(0.f, 0.f);
                         if (RAGGED && i >= r) xx = make_float2(0.f, 0.f);
-                        if (t.K == e0 && lane == jl) nrow[i < WD ? i : WD - 1] = make_float2(xx.x, -xx.y);
+                        if (t.K == e0 && lane == jl) nrow[i] = make_float2(xx.x, -xx.y);
                         cfma(racc[rr], xx, vk);
                         if (k == i) {
                             kl = fmaf(-xx.x, vi.x * vi.x + vi.y * vi.y, kl);
@@ -341,19 +349,27 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
                     for (int rr = 0; rr < TR; ++rr) racc[rr] = make_float2(0.f, 0.f);
                 }
             };
-            float2 xa[TR], xb[TR];
-            TileIt t0 = first(), t1;
-            if (t0.valid) {
-                load(t0, xa);
-                while (true) {
-                    t1 = advance(t0);
-                    if (t1.valid) load(t1, xb);
+            if (DB) {
+                float2 xa[TR], xb[TR];
+                TileIt t0 = first(), t1;
+                if (t0.valid) {
+                    load(t0, xa);
+                    while (true) {
+                        t1 = advance(t0);
+                        if (t1.valid) load(t1, xb);
+                        process(t0, xa);
+                        if (!t1.valid) break;
+                        t0 = advance(t1);
+                        if (t0.valid) load(t0, xa);
+                        process(t1, xb);
+                        if (!t0.valid) break;
+                    }
+                }
+            } else {
+                float2 xa[TR];
+                for (TileIt t0 = first(); t0.valid; t0 = advance(t0)) {
+                    load(t0, xa);
                     process(t0, xa);
-                    if (!t1.valid) break;
-                    t0 = advance(t1);
-                    if (t0.valid) load(t0, xa);
-                    process(t1, xb);
-                    if (!t0.valid) break;
                 }
             }
             kacc = warp_sum(kl);
@@ -443,29 +459,36 @@ __global__ void __launch_bounds__(SD_THREADS, 1)
     }
 }
 
-template <int EPL, int TR, int NB, bool RAGGED>
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED>
 int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
                     float* tau, float2* ph) {
     constexpr int WD = EPL * 32;
+    const size_t budget = NT == 512 ? (size_t)VK_SMEM_BUDGET : (size_t)110 * 1024;   // two CTAs per SM
     const size_t vec = (size_t)(5 + 2 * NB) * WD * sizeof(float2);
-    const size_t partb = (size_t)SD_WARPS * WD * sizeof(float2);
-    int nts = (int)sqrt((double)(VK_SMEM_BUDGET - vec) / sizeof(float2));
+    const size_t partb = (size_t)(NT / 32) * WD * sizeof(float2);
+    int nts = budget > vec ? (int)sqrt((double)(budget - vec) / sizeof(float2)) : 0;
     if (nts > r) nts = r;
     size_t tb = (size_t)nts * nts * sizeof(float2);
     if (tb < partb) tb = partb;
     const size_t smem = vec + tb;
-    VK_CUDA(h, cudaFuncSetAttribute(tridiag_symdefer_kernel<EPL, TR, NB, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    tridiag_symdefer_kernel<EPL, TR, NB, RAGGED><<<B, SD_THREADS, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
+    auto kern = tridiag_symdefer_kernel<EPL, TR, NB, NT, DB, RAGGED>;
+    VK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, NT, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
 
+// variant: 0 = one matrix per SM (512 threads, 8-row tiles, double buffer), 1 = two per SM (256 threads, 16-row tiles)
 template <int EPL>
 int launch_symdefer_r(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
-                      float* tau, float2* ph) {
-    if (r % 32 == 0) return launch_symdefer<EPL, 8, 8, false>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
-    return launch_symdefer<EPL, 8, 8, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+                      float* tau, float2* ph, int variant) {
+    const bool ragged = (r % 32) != 0;
+    if (variant == 1) {
+        if (ragged) return launch_symdefer<EPL, 16, 6, 256, false, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+        return launch_symdefer<EPL, 16, 6, 256, false, false>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    }
+    if (ragged) return launch_symdefer<EPL, 8, 8, 512, true, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    return launch_symdefer<EPL, 8, 8, 512, true, false>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
 }
 
 }  // namespace
@@ -474,7 +497,11 @@ bool vk_tridiag_symdefer_supported(int r) { return r > 128 && r <= 512; }
 
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,
                                float* e, float* tau, float2* ph) {
-    if (r <= 256) return launch_symdefer_r<8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
-    if (r <= 384) return launch_symdefer_r<12>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
-    return launch_symdefer_r<16>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    // two matrices per SM once there are more matrices than SMs ("tridiag_variant": 1 / 2 force one / two per SM)
+    int variant = B > h->num_sms ? 1 : 0;
+    if (h->tridiag_variant == 1) variant = 0;
+    if (h->tridiag_variant == 2) variant = 1;
+    if (r <= 256) return launch_symdefer_r<8>(h, st, W, B, r, ld, wstride, d, e, tau, ph, variant);
+    if (r <= 384) return launch_symdefer_r<12>(h, st, W, B, r, ld, wstride, d, e, tau, ph, variant);
+    return launch_symdefer_r<16>(h, st, W, B, r, ld, wstride, d, e, tau, ph, variant);
 }
