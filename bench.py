@@ -44,13 +44,17 @@ WORKLOADS = {
     "kat7": (28, 4, 256, 1024, dict(compressionrank=8), "configs[1]: synthetic KAT-7 shape 28 bl x 4 corr x 256 x 1024, k=8"),
     "meerkat": (260, 4, 512, 4096, dict(decorrelation=0.99),
                 "configs[2]: MeerKAT-64 shape, 260-baseline shard (1/8 of 2080) x 4 corr x 512 x 4096, decorrelation 0.99"),
-    "small": (2080, 4, 64, 64, dict(compressionrank=8), "configs[3]: 2080 bl x 4 corr x 64 x 64, one-sided Jacobi path"),
+    "small": (2080, 4, 64, 64, dict(compressionrank=8), "configs[3]: 2080 bl x 4 corr x 64 x 64, default route (Gram product + "
+              "warp-level tridiagonalisation; the ill-conditioned-set safeguard uses the one-sided Jacobi kernels)"),
+    "small_jacobi": (2080, 4, 64, 64, dict(compressionrank=8), "configs[3]: 2080 bl x 4 corr x 64 x 64, one-sided Jacobi path "
+                     "as the configuration names it (option small_impl = 1)"),
 }
-CUBES_PER_STEP = {"kat7": 32, "meerkat": 1, "small": 8}
-NCUBES = {"kat7": 4, "meerkat": 1, "small": 4}
+CUBES_PER_STEP = {"kat7": 32, "meerkat": 1, "small": 8, "small_jacobi": 8}
+NCUBES = {"kat7": 4, "meerkat": 1, "small": 4, "small_jacobi": 4}
+OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload runs with (reset afterwards)
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
 # (one CTA per matrix: 112 of 148 SMs at the KAT-7 shape, host polls in between) overlaps the other stages of the next
-HANDLES = {"kat7": 2, "meerkat": 1, "small": 2}
+HANDLES = {"kat7": 2, "meerkat": 1, "small": 2, "small_jacobi": 2}
 E2E_THREADS = 3
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
 
@@ -336,6 +340,9 @@ def run_workload(eng, Engine, torch, dist, dev, world, rank, name, steps, warmup
 
     nh = HANDLES[name]
     engines = [eng] + [Engine(eng.device) for _ in range(nh - 1)]
+    for e_ in engines:
+        for k_, v_ in OPTIONS.get(name, {}).items():
+            e_.set_option(k_, v_)
     streams = [torch.cuda.Stream(device=dev) for _ in range(nh)]
     facs = [fac] + [tuple(torch.empty_like(x) for x in fac) for _ in range(nh - 1)]
     outs = [out] + [torch.empty_like(out) for _ in range(nh - 1)]
@@ -412,6 +419,8 @@ def run_workload(eng, Engine, torch, dist, dev, world, rank, name, steps, warmup
         for k_, v_ in eng.last_eig_ms().items():
             eig_acc[k_] = eig_acc.get(k_, 0.0) + v_ / nst
     eng.set_option("stage_timing", 0)
+    for k_ in OPTIONS.get(name, {}):
+        eng.set_option(k_, 0)
     last_cube = (nst - 1) % ncubes
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -692,7 +701,7 @@ def run_ours(args):
     del w
     torch.cuda.empty_cache()
     if args.extras:
-        for name in ("meerkat", "small"):
+        for name in ("meerkat", "small", "small_jacobi"):
             if name == args.workload:
                 continue
             log("extra " + name)

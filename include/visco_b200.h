@@ -119,7 +119,9 @@ int vk_eigh_jacobi_batched(vk_handle h, void* W_dev, int B, int r, float* lambda
  * min(m,n) * (max(m,n) + min(m,n)) * 8 bytes <= 200 KiB). Full factors, sorted: U [B][m][r], S [B][r], Vt [B][r][n]. */
 int vk_svd_jacobi_small_batched(vk_handle h, const void* A_dev, int B, int m, int n, void* U_dev, float* S_dev,
                                 void* Vt_dev, int32_t* info_dev);
-/* 1 if (m, n) takes the direct small-matrix path inside vk_compress_batched, else 0 (Gram path). */
+/* 1 if (m, n) takes the one-sided Jacobi small-matrix path inside vk_compress_batched with default options, else 0
+ * (Gram path). Default: eligible shapes with min(m,n) <= 32; option "small_impl" = 1 takes it for every eligible shape
+ * (min(m,n) <= 64, e.g. BASELINE configs[3]), 2 never. */
 int vk_uses_small_path(int m, int n);
 /* 1 if the tcgen05 Gram kernel handles (m, n, side), else 0 (SIMT Gram). */
 int vk_gram_uses_tcgen05(int m, int n, int side);

@@ -36,7 +36,8 @@ def test_library_exports_every_declared_symbol():
 def test_path_selection_is_pure_host_logic():
     from visco_b200 import _lib
     lib = _lib.load()
-    assert lib.vk_uses_small_path(64, 64) == 1          # BASELINE config 4
+    assert lib.vk_uses_small_path(64, 64) == 0          # BASELINE config 4: Gram path by default ("small_impl" = 1: Jacobi)
+    assert lib.vk_uses_small_path(32, 64) == 1
     assert lib.vk_uses_small_path(360, 16) == 1         # sample MS
     assert lib.vk_uses_small_path(16, 360) == 1
     assert lib.vk_uses_small_path(256, 1024) == 0       # config 2 -> Gram path

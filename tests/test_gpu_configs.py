@@ -60,14 +60,20 @@ def test_c3_shape_fixed_rank(eng, torch):
 
 
 # ------------------------------------------------------------------------------------------------ C4
+@pytest.mark.parametrize("small_impl", [1, 0])
 @pytest.mark.parametrize("kw", [dict(compressionrank=8), dict(decorrelation=0.95)])
-def test_c4_small_matrix_batch(eng, torch, kw):
-    """BASELINE configs[3]: 64 x 64 matrices through the one-sided Jacobi path, a 520-matrix batch (130 baselines x 4),
-    every matrix checked against the oracle."""
+def test_c4_small_matrix_batch(eng, torch, kw, small_impl):
+    """BASELINE configs[3]: 64 x 64 matrices, a 520-matrix batch (130 baselines x 4), every matrix checked against the
+    oracle - through the one-sided Jacobi path the configuration names ("small_impl" = 1) and through the default route
+    (Gram product + warp-level tridiagonalisation, tridiag_small.cu)."""
     nbl, ncorr, m, n = 130, 4, 64, 64
-    assert eng.uses_small_path(m, n)
+    assert not eng.uses_small_path(m, n) and eng.uses_small_path(32, 64)
     A = _device_cube(eng, torch, nbl, ncorr, m, n, nbl_total=2080, bl_offset=975)
-    U, S, Vt, ranks, stats = eng.compress(A, **kw)
+    eng.set_option("small_impl", small_impl)
+    try:
+        U, S, Vt, ranks, stats = eng.compress(A, **kw)
+    finally:
+        eng.set_option("small_impl", 0)
     out = eng.reconstruct(U, S, Vt, ranks)
     torch.cuda.synchronize()
     Ah, Uh, Sh, Vh, rk, st, oh = (x.cpu().numpy() for x in (A, U, S, Vt, ranks, stats, out))

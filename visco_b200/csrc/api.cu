@@ -14,11 +14,23 @@ struct WsLayout {
     size_t W, perm, inv, gscale, sweeps, done, offmax, active, nonfinite, norm2, xbuf, eig, total;
 };
 
-bool small_path(int m, int n) {
+// the one-sided (Hestenes) Jacobi kernels hold the whole problem in one CTA's shared memory
+bool small_eligible(int m, int n) {
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
     if (r > 64) return false;
     return (size_t)(r + (r & 1)) * (size_t)(L + r) * sizeof(float2) + 1024 <= VK_SMEM_BUDGET;
+}
+// ... and are taken ("small_impl" 0, the default) up to r = 32; above that the Gram path with the warp-level
+// tridiagonalisation (tridiag_small.cu) is 5x faster (BASELINE configs[3], 8320 matrices of 64 x 64: 4.2 vs 24.7 ms) and
+// the ill-conditioned-set safeguard still sends what needs it through the Jacobi kernels. "small_impl" 1: always when
+// eligible (the configuration BASELINE configs[3] names), 2: never.
+bool small_path(const vk_context* h, int m, int n) {
+    if (!small_eligible(m, n)) return false;
+    const int impl = h ? h->small_impl : 0;
+    if (impl == 1) return true;
+    if (impl == 2) return false;
+    return (m < n ? m : n) <= 32;
 }
 
 // eigensolver of the Gram path: 1 = cyclic Jacobi (with the blocked subspace iteration for small fixed ranks),
@@ -26,17 +38,17 @@ bool small_path(int m, int n) {
 bool use_qr(const vk_context* h, int m, int n, int fixed_rank = 0) {
     (void)fixed_rank;
     const int r = m < n ? m : n;
-    if (!h || small_path(m, n) || !vk_eigqr_supported(r) || h->eig_impl == 1) return false;
+    if (!h || small_path(h, m, n) || !vk_eigqr_supported(r) || h->eig_impl == 1) return false;
     return true;
 }
 
-WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false, bool direct = false) {
+WsLayout ws_layout(const vk_context* h, int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = false, bool direct = false) {
     if (gchunk < chunk) gchunk = chunk;
     const int r = m < n ? m : n;
     const int L = m < n ? n : m;
     WsLayout w;
     size_t off = 0;
-    const size_t wbytes = (small_path(m, n) || direct) ? (size_t)gchunk * r * (L + r) * sizeof(float2)
+    const size_t wbytes = (small_path(h, m, n) || direct) ? (size_t)gchunk * r * (L + r) * sizeof(float2)
                                                        : (size_t)gchunk * r * r * sizeof(float2);
     w.W = off, off += align_up(wbytes);
     w.perm = off, off += align_up((size_t)chunk * r * 4);
@@ -50,7 +62,7 @@ WsLayout ws_layout(int chunk, int m, int n, int kmax, int gchunk = 0, bool qr = 
     w.norm2 = off, off += align_up((size_t)chunk * kmax * 4);
     // K-major copy of conj(U_k)^T for the tcgen05 V-formation (wide Gram path, k > 8)
     w.xbuf = off;
-    if (!small_path(m, n) && !direct && m <= n && vk_cgemm_tc_supported(m, n, kmax))
+    if (!small_path(h, m, n) && !direct && m <= n && vk_cgemm_tc_supported(m, n, kmax))
         off += align_up((size_t)chunk * kmax * m * 8);
     w.eig = off;
     if (qr) off += align_up(vk_eigqr_scratch_bytes(chunk, r));
@@ -70,7 +82,7 @@ int auto_chunk(const vk_context* h, int B, int m, int n, bool qr) {
         if (c > (size_t)B) c = B;
         return (int)c;
     }
-    const size_t per = small_path(m, n) ? (size_t)r * (L + r) * 8 : (size_t)r * r * 8;
+    const size_t per = small_path(h, m, n) ? (size_t)r * (L + r) * 8 : (size_t)r * r * 8;
     // keep the Jacobi working set of one internal pass inside ~half of the 126 MB L2, but never below a few waves
     size_t c = (64u << 20) / (per ? per : 1);
     if (c < 32) c = 32;
@@ -80,8 +92,8 @@ int auto_chunk(const vk_context* h, int B, int m, int n, bool qr) {
 
 // The Gram product is launched over a super-chunk of several Jacobi chunks: one launch then covers many waves of
 // tiles (a 32-matrix chunk of 512 x 4096 matrices is only 2.2 waves of 148 CTAs, a 28 % quantisation loss).
-int gram_chunk(int B, int chunk, int m, int n) {
-    if (small_path(m, n)) return chunk;
+int gram_chunk(const vk_context* h, int B, int chunk, int m, int n) {
+    if (small_path(h, m, n)) return chunk;
     const int r = m < n ? m : n;
     size_t cap = (512u << 20) / ((size_t)r * r * 8);  // at most 512 MB of Gram matrices at a time
     if (cap < 1) cap = 1;
@@ -144,7 +156,7 @@ int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixe
     // sub0: index of this chunk's first matrix inside the Gram super-chunk (W and gscale are laid out per super-chunk)
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
-    const bool no_gram = small_path(m, n) || direct;  // one-sided Jacobi on the matrix itself
+    const bool no_gram = small_path(h, m, n) || direct;  // one-sided Jacobi on the matrix itself
     float2* W = reinterpret_cast<float2*>(ws + L.W) + (no_gram ? 0 : (size_t)sub0 * r * r);
     int32_t* perm = reinterpret_cast<int32_t*>(ws + L.perm);
     float* inv = reinterpret_cast<float*>(ws + L.inv);
@@ -248,11 +260,11 @@ int redo_ill_conditioned(vk_context* h, const float2* A, int B, int m, int n, in
         if (hf[b]) idx.push_back(b);
     const size_t bA = (size_t)m * n * 8, bU = (size_t)m * kmax * 8, bS = (size_t)kmax * 4, bV = (size_t)kmax * n * 8;
     const size_t per = align_up(bA) + align_up(bU) + align_up(bS) + align_up(bV) + 512 +
-                       ws_layout(1, m, n, kmax, 1, false, true).total;
+                       ws_layout(h, 1, m, n, kmax, 1, false, true).total;
     int cap = (int)(((size_t)2 << 30) / per);
     if (cap < 1) cap = 1;
     if (cap > (int)idx.size()) cap = (int)idx.size();
-    const WsLayout Ld = ws_layout(cap, m, n, kmax, cap, false, true);
+    const WsLayout Ld = ws_layout(h, cap, m, n, kmax, cap, false, true);
     const size_t oA = 0, oU = oA + align_up(bA * cap), oS = oU + align_up(bU * cap), oV = oS + align_up(bS * cap),
                  oR = oV + align_up(bV * cap), oT = oR + align_up((size_t)cap * 4), oW = oT + align_up((size_t)cap * 16);
     if ((rc = ensure(h, &h->ws2, &h->ws2_bytes, oW + Ld.total))) return rc;
@@ -410,6 +422,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "tridiag_impl")
         h->tridiag_impl = (int)v;
+    else if (k == "small_impl")
+        h->small_impl = (int)v;
     else if (k == "tridiag_variant")
         h->tridiag_variant = (int)v;
     else if (k == "eigvec_impl")
@@ -434,13 +448,13 @@ size_t vk_workspace_bytes(vk_handle h, int B, int m, int n, int kmax) {
         if (qr && !use_qr(h, m, n, 0)) continue;
         int chunk = (h && h->chunk > 0) ? h->chunk : auto_chunk(h, B, m, n, qr);
         if (chunk > B) chunk = B;
-        const size_t t = ws_layout(chunk, m, n, kmax, gram_chunk(B, chunk, m, n), qr).total;
+        const size_t t = ws_layout(h, chunk, m, n, kmax, gram_chunk(h, B, chunk, m, n), qr).total;
         if (t > need) need = t;
     }
     return need;
 }
 
-int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(m, n)) ? 1 : 0; }
+int vk_uses_small_path(int m, int n) { return (m >= 1 && n >= 1 && small_path(nullptr, m, n)) ? 1 : 0; }
 int vk_gram_uses_tcgen05(int m, int n, int side) { return vk_gram_tc_supported(m, n, side) ? 1 : 0; }
 
 int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
@@ -459,8 +473,8 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     const bool qr = use_qr(h, m, n, fixed_rank);
     int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n, qr);
     if (chunk > B) chunk = B;
-    const int gchunk = gram_chunk(B, chunk, m, n);
-    const WsLayout L = ws_layout(chunk, m, n, kmax, gchunk, qr);
+    const int gchunk = gram_chunk(h, B, chunk, m, n);
+    const WsLayout L = ws_layout(h, chunk, m, n, kmax, gchunk, qr);
     unsigned char* wsp = static_cast<unsigned char*>(ws);
     if (!wsp) {
         if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total))) return rc;
@@ -475,7 +489,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     const float2* Ap = static_cast<const float2*>(A);
     float2* Up = static_cast<float2*>(U);
     float2* Vp = static_cast<float2*>(Vt);
-    const bool gram_path = !small_path(m, n);
+    const bool gram_path = !small_path(h, m, n);
     for (int g0 = 0; g0 < B; g0 += gchunk) {
         const int ng = (B - g0) < gchunk ? (B - g0) : gchunk;
         if (gram_path) {
@@ -722,13 +736,21 @@ int vk_svd_jacobi_small_batched(vk_handle h, const void* A, int B, int m, int n,
                                 int32_t* info) {
     if (!h) return VK_EINVAL;
     if (B < 0 || m < 1 || n < 1 || !A || !U || !S || !Vt) return vk_fail(h, VK_EINVAL, "bad argument");
-    if (!small_path(m, n)) return vk_fail(h, VK_EINVAL, "shape is not eligible for the small-matrix path");
+    if (!small_eligible(m, n)) return vk_fail(h, VK_EINVAL, "shape is not eligible for the small-matrix path");
     if (B == 0) return VK_OK;
     VK_CUDA(h, cudaSetDevice(h->device));
     const int r = m < n ? m : n;
     int rc;
+    // this entry point IS the one-sided Jacobi path, whatever the routing option says
+    const int save_impl = h->small_impl;
+    h->small_impl = 1;
+    struct Restore {
+        vk_context* h;
+        int v;
+        ~Restore() { h->small_impl = v; }
+    } restore{h, save_impl};
     // ranks + stats scratch live behind the regular workspace
-    const WsLayout L = ws_layout(B, m, n, r);
+    const WsLayout L = ws_layout(h, B, m, n, r);
     const size_t extra = align_up((size_t)B * 4) + align_up((size_t)B * 16);
     if ((rc = ensure(h, &h->ws, &h->ws_bytes, L.total + extra))) return rc;
     unsigned char* ws = static_cast<unsigned char*>(h->ws);

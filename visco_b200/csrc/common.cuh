@@ -42,6 +42,7 @@ struct vk_context {
     int topk = 0;            // 0 = auto (subspace iteration for compressionrank <= 4), 1 = full Jacobi only, 2 = up to rank 8
     int gemm_impl = 0;       // 0 = auto (tcgen05 GEMM for k > 8 where the shape allows), 1 = SIMT only
     int tridiag_variant = 0;  // tridiag_sym.cu: 0 = by batch size, 1 = one matrix per SM, 2 = two per SM
+    int small_impl = 0;       // one-sided Jacobi path: 0 = for r <= 32, 1 = whenever the matrix fits one CTA, 2 = never
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
@@ -130,6 +131,10 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
 bool vk_tridiag_symdefer_supported(int r);
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,
                                float* e, float* tau, float2* ph);
+// r <= 64: one warp per matrix, matrix in shared memory (tridiag_small.cu)
+bool vk_tridiag_small_supported(int r);
+int vk_launch_tridiag_small(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
+                            float* tau, float2* ph);
 bool vk_topk_supported(int r, int fixed_rank, bool force);
 int vk_launch_topk(vk_context* h, float2* W, int B, int r, int fixed_rank, int32_t* done_dev, int32_t* sweeps_dev);
 

@@ -1925,6 +1925,7 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     else if (r > 128 && r <= 256 && h->tridiag_impl == 2) rc = launch_tridiag_defer<8, 4, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 384 && r <= 512 && h->tridiag_impl != 1) rc = launch_tridiag_defer<16, 2, 8>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r > 256 && r <= 512 && h->jacobi_generic != 2) rc = launch_tridiag_sym<16, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    else if (r <= 64 && h->tridiag_impl == 0) rc = vk_launch_tridiag_small(h, st, W, B, r, ld, wstride, d, e, tau, ph);  // one warp per matrix
     else if (r <= 64) rc = launch_tridiag<2, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 128) rc = launch_tridiag<4, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else if (r <= 256) rc = launch_tridiag<8, 4>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
