@@ -422,6 +422,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "tridiag_impl")
         h->tridiag_impl = (int)v;
+    else if (k == "factors_impl")
+        h->factors_impl = (int)v;
     else if (k == "small_impl")
         h->small_impl = (int)v;
     else if (k == "tridiag_variant")

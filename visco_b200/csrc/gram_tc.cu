@@ -92,6 +92,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
     }
     const int J = I + tile;
     const int KB = (n2 + KB_FLOATS - 1) / KB_FLOATS;
+    // diagonal tile: the A operand IS the first half of the B operand (R_J) - it is neither loaded nor converted a second
+    // time (64 of the 304 KB of shared-memory traffic per K-block, which is what bounds this kernel)
+    const bool diag = I == J;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
@@ -128,8 +131,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
                 const uint32_t use = kb / NSTAGE;
                 mbar_wait(bar_empty + 8 * s, (use & 1) ^ 1);
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(bar_raw + 8 * s, 2 * A_TILE_BYTES);
-                tma_load_3d(st + OFF_A_HI, &tmap, bar_raw + 8 * s, kb * KB_FLOATS, I * TILE, b);
+                mbar_arrive_expect_tx(bar_raw + 8 * s, diag ? A_TILE_BYTES : 2 * A_TILE_BYTES);
+                if (!diag) tma_load_3d(st + OFF_A_HI, &tmap, bar_raw + 8 * s, kb * KB_FLOATS, I * TILE, b);
                 tma_load_3d(st + OFF_B_HI, &tmap, bar_raw + 8 * s, kb * KB_FLOATS, J * TILE, b);
             }
         }
@@ -150,7 +153,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                const uint64_t a_hi = desc_kmajor_sw128(st + OFF_A_HI), a_lo = desc_kmajor_sw128(st + OFF_A_LO);
+                const uint64_t a_hi = desc_kmajor_sw128(st + (diag ? OFF_B_HI : OFF_A_HI)),
+                               a_lo = desc_kmajor_sw128(st + (diag ? OFF_B_LO : OFF_A_LO));
                 const uint64_t b_hi = desc_kmajor_sw128(st + OFF_B_HI), b_lo = desc_kmajor_sw128(st + OFF_B_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
@@ -189,9 +193,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
 #pragma unroll 2
             for (int i = 0; i < CH / NUM_CONVERTERS; ++i) {
                 const int c = ct + i * NUM_CONVERTERS;
-                const Split4 sa = split4(a_hi[c]);
-                a_hi[c] = sa.hi;
-                a_lo[c] = sa.lo;
+                if (!diag) {
+                    const Split4 sa = split4(a_hi[c]);
+                    a_hi[c] = sa.hi;
+                    a_lo[c] = sa.lo;
+                }
                 const Split4 sb = split4(b_hi[c]);
                 b_hi[c] = sb.hi;
                 b_lo[c] = sb.lo;

@@ -1,6 +1,8 @@
 // SIMT stages of the hot path (sm_100a): Gram product for shapes the tcgen05 kernel does not take, Gram
 // normalisation, small-matrix packing, singular-value selection / rank truncation, factor formation, rank-k
 // reconstruction, and the benchmark generator. Reference call sites are cited at each launcher.
+#include <cooperative_groups.h>
+
 #include "cgemm.cuh"
 
 namespace {
@@ -460,6 +462,186 @@ static int launch_formv_smallk(vk_context* h, const float2* A, const float2* W, 
     return VK_OK;
 }
 
+// Fused factor formation for small ranks on the wide Gram path (north_star item (c)): ONE launch produces U_k, the refined
+// singular values, the normalised Vt rows and the retained energy. The channels of a matrix are shared by a thread-block
+// cluster (one CTA per 256-channel strip, up to 8); every CTA streams its strip of A once (as formv_smallk_kernel), the
+// squared row norms are exchanged through distributed shared memory, and the rows leave the registers already divided by
+// sigma - no atomics, no second pass over Vt, no memset, deterministic summation order.
+// RS: the rows of A are split over RS groups of 128 threads (more loads in flight: with one group the kernel ran at
+// 1.9 TB/s, 12 warps per SM, latency bound); the groups' partial sums meet in shared memory.
+template <int KC, int RS>
+__global__ void __launch_bounds__(128 * RS)
+factors_fused_kernel(const float2* __restrict__ A, const float2* __restrict__ W, const int32_t* __restrict__ perm,
+                     const float* __restrict__ inv, const int32_t* __restrict__ ranks, float2* __restrict__ U,
+                     float* __restrict__ S, float2* __restrict__ Vt, float* __restrict__ stats, int m, int n, int kmax,
+                     int strips) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int NT = 128 * RS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* xs = reinterpret_cast<float4*>(smem_raw);                     // [m][KC]
+    float4* xch = xs + (size_t)m * KC;                                    // [RS - 1][KC][128] partial sums of the other groups
+    __shared__ float red[4][KC];                       // per warp: squared norms of this CTA's part of every row
+    __shared__ float sig[KC];
+    const int strip = (int)cluster.block_rank();
+    const int b = blockIdx.x / strips;
+    const int k = min(ranks[b], kmax);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch = threadIdx.x & 127, rs = threadIdx.x >> 7;
+    __shared__ int sp[KC];
+    __shared__ float sf[KC];
+    const int v0 = strip * 256 + ch * 2;
+    const bool live = v0 < n;
+    const int mq = (m + RS - 1) / RS;
+    const int t0 = rs * mq, t1 = min(m, t0 + mq);
+    const float2* a = A + (size_t)b * m * n + v0;
+    constexpr int G = 8;
+    float4 cur[G], nxt[G];
+    // the first row group of A is on its way before anything else happens
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        cur[g] = (live && t0 + g < t1) ? __ldcs(reinterpret_cast<const float4*>(a + (size_t)(t0 + g) * n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < KC) {
+        const bool on = (int)threadIdx.x < k;
+        sp[threadIdx.x] = on ? perm[(size_t)b * m + threadIdx.x] : 0;
+        sf[threadIdx.x] = on ? inv[(size_t)b * m + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    // coefficients conj(u_c[t]) = conj(W[perm c][t]) inv[c], expanded for the packed FMAs (independent loads: all in flight)
+#pragma unroll 4
+    for (int e = threadIdx.x; e < m * KC; e += NT) {
+        const int c = e / m, t = e - c * m;  // t fastest: coalesced reads of the eigenvector rows
+        const float f = sf[c];
+        const float2 w = W[((size_t)b * m + sp[c]) * m + t];
+        const float2 x = make_float2(w.x * f, -w.y * f);
+        xs[t * KC + c] = make_float4(x.x, x.x, -x.y, x.y);
+    }
+    __syncthreads();
+    float2 acc0[KC], acc1[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) acc0[c] = acc1[c] = make_float2(0.f, 0.f);
+    if (live) {
+        // register double buffer: the eight loads of the next row group are in flight while this one is consumed (left
+        // to the compiler, the loads trailed their uses one by one: every first use stalled, 1.9 TB/s)
+        for (int tb = t0; tb < t1; tb += G) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                nxt[g] = (tb + G + g < t1) ? __ldcs(reinterpret_cast<const float4*>(a + (size_t)(tb + G + g) * n))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int t = min(tb + g, m - 1);         // rows past the end carry zeros
+                const float4 av = cur[g];
+                const float2 a0 = make_float2(av.x, av.y), a0s = make_float2(av.y, av.x);
+                const float2 a1 = make_float2(av.z, av.w), a1s = make_float2(av.w, av.z);
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const float4 x = xs[t * KC + c];
+                    const float2 xa = make_float2(x.x, x.y), xb = make_float2(x.z, x.w);
+                    acc0[c] = __ffma2_rn(xa, a0, acc0[c]);
+                    acc0[c] = __ffma2_rn(xb, a0s, acc0[c]);
+                    acc1[c] = __ffma2_rn(xa, a1, acc1[c]);
+                    acc1[c] = __ffma2_rn(xb, a1s, acc1[c]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) cur[g] = nxt[g];
+        }
+    }
+    if (RS > 1) {
+        if (rs > 0) {
+#pragma unroll
+            for (int c = 0; c < KC; ++c)
+                xch[((size_t)(rs - 1) * KC + c) * 128 + ch] = make_float4(acc0[c].x, acc0[c].y, acc1[c].x, acc1[c].y);
+        }
+        __syncthreads();
+        if (rs == 0) {
+#pragma unroll
+            for (int g = 0; g < RS - 1; ++g)
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const float4 o = xch[((size_t)g * KC + c) * 128 + ch];
+                    acc0[c].x += o.x, acc0[c].y += o.y, acc1[c].x += o.z, acc1[c].y += o.w;
+                }
+        }
+    }
+    if (rs == 0) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            float s2 = (c < k && live) ? (acc0[c].x * acc0[c].x + acc0[c].y * acc0[c].y + acc1[c].x * acc1[c].x + acc1[c].y * acc1[c].y) : 0.f;
+            s2 = warp_sum(s2);
+            if (lane == 0) red[warp][c] = s2;
+        }
+    }
+    cluster.sync();
+    // sigma_c = || A^H u_c ||: the strips' parts in rank order, the warps' parts in warp order
+    if (threadIdx.x < KC) {
+        float tot = 0.f;
+        for (int rk = 0; rk < strips; ++rk) {
+            const float* peer = cluster.map_shared_rank(&red[0][0], rk);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) tot += peer[w * KC + threadIdx.x];
+        }
+        sig[threadIdx.x] = sqrtf(tot);
+    }
+    __syncthreads();
+    if (rs == 0) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            if (c < kmax && live) {
+                const float sg = sig[c];
+                const float f = (c < k && sg > 0.f) ? 1.f / sg : 0.f;
+                *reinterpret_cast<float4*>(Vt + ((size_t)b * kmax + c) * n + v0) =
+                    make_float4(acc0[c].x * f, acc0[c].y * f, acc1[c].x * f, acc1[c].y * f);
+            }
+        }
+    }
+    if (strip == 0) {
+        if (threadIdx.x < k) S[(size_t)b * kmax + threadIdx.x] = sig[threadIdx.x];
+        if (threadIdx.x == 0) {
+            double e = 0.0;
+            for (int c = 0; c < k; ++c) e += (double)sig[c] * (double)sig[c];
+            stats[4 * b + 1] = (float)e;
+        }
+        // U[t][c] = u_c[t] = conj of what xs holds; zero beyond the rank
+        float2* Ub = U + (size_t)b * m * kmax;
+        for (int e = threadIdx.x; e < m * kmax; e += NT) {
+            const int t = e / kmax, c = e - t * kmax;
+            const float4 x = xs[t * KC + c];
+            Ub[e] = c < k ? make_float2(x.x, -x.w) : make_float2(0.f, 0.f);
+        }
+    }
+    cluster.sync();   // nobody leaves while a peer may still read its partial sums
+}
+
+template <int KC>
+static int launch_factors_fused(vk_context* h, const float2* A, const float2* W, const int32_t* perm, const float* inv,
+                                const int32_t* ranks, float2* U, float* S, float2* Vt, float* stats, int B, int m, int n,
+                                int kmax) {
+    const int strips = (n + 255) / 256;
+    const long long nblocks = (long long)B * strips;
+    if (nblocks > 0x7fffffffLL) return vk_fail(h, VK_EINVAL, "factors: grid too large");
+    constexpr int RS = 1;
+    const size_t smem = (size_t)m * KC * sizeof(float4) + (size_t)(RS - 1) * KC * 128 * sizeof(float4);
+    if (smem > 48 * 1024)
+        VK_CUDA(h, cudaFuncSetAttribute(factors_fused_kernel<KC, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblocks, 1, 1);
+    cfg.blockDim = dim3(128 * RS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)strips;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VK_CUDA(h, cudaLaunchKernelEx(&cfg, factors_fused_kernel<KC, RS>, A, W, perm, inv, ranks, U, S, Vt, stats, m, n, kmax, strips));
+    h->launches += 1;
+    return VK_OK;
+}
+
 struct FormUOp {  // U[t][c] = sum_j A[t][j] * W[perm c][j] inv[c]                    (tall, r = n)
     const float2* A;
     const float2* W;
@@ -832,6 +1014,15 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
                            const int32_t* perm_dev, const float* inv_dev, const int32_t* ranks_dev, float* norm2_dev,
                            float2* U, float* S, float2* Vt, float* stats_dev, float2* xbuf) {
     int rc;
+    if (side == 0 && kmax <= 16 && (n % 2) == 0 && (n + 255) / 256 <= 8 && h->factors_impl == 0 && !h->recon_generic &&
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16) == 0 &&
+        (size_t)(m + 3 * 128) * (kmax <= 8 ? 8 : 16) * sizeof(float4) <= VK_SMEM_BUDGET) {
+        // small rank, wide matrix: everything in one launch (a cluster of up to eight 256-channel strips per matrix)
+        if (kmax <= 2) return launch_factors_fused<2>(h, A, W, perm_dev, inv_dev, ranks_dev, U, S, Vt, stats_dev, B, m, n, kmax);
+        if (kmax <= 4) return launch_factors_fused<4>(h, A, W, perm_dev, inv_dev, ranks_dev, U, S, Vt, stats_dev, B, m, n, kmax);
+        if (kmax <= 8) return launch_factors_fused<8>(h, A, W, perm_dev, inv_dev, ranks_dev, U, S, Vt, stats_dev, B, m, n, kmax);
+        return launch_factors_fused<16>(h, A, W, perm_dev, inv_dev, ranks_dev, U, S, Vt, stats_dev, B, m, n, kmax);
+    }
     VK_CUDA(h, cudaMemsetAsync(norm2_dev, 0, sizeof(float) * (size_t)B * kmax, h->stream));
     if (side == 0) {
         const int r = m;
