@@ -55,7 +55,7 @@ OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload run
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
 # (one CTA per matrix: 112 of 148 SMs at the KAT-7 shape, host polls in between) overlaps the other stages of the next
 HANDLES = {"kat7": 2, "meerkat": 1, "small": 2, "small_jacobi": 2}
-E2E_THREADS = 3
+E2E_THREADS = int(os.environ.get("VISCO_E2E_THREADS", "0"))   # 0: six, or as many as the rank's share of the host cores allows
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
 
 
@@ -477,7 +477,8 @@ def dominant_roofline(w, kbar, pk, share_of):
     B, m, n = w["B"], w["m"], w["n"]
     r = min(m, n)
     eg, st = w["eig_ms"], w["stage_ms"]
-    cand = {"tridiag_kernel (Householder tridiagonalisation, one CTA per matrix)": eg.get("tridiag", 0.0),
+    tri_name = "tridiag_symdefer_kernel" if 128 < r <= 512 else ("tridiag_small_kernel" if r <= 64 else "tridiag_kernel")
+    cand = {tri_name + " (Householder tridiagonalisation, one CTA per matrix)": eg.get("tridiag", 0.0),
             "gram_tc_kernel (tcgen05 3xTF32 Gram product)": st.get("gram", 0.0),
             "formq_kernel (reflector accumulation)": eg.get("reflectors", 0.0),
             "factor formation (formv / cgemm_tc)": st.get("factors", 0.0),
@@ -496,13 +497,18 @@ def dominant_roofline(w, kbar, pk, share_of):
          "note": "SURVEY 8(d) Bytes_compress (A read once, factors written once) of the matrices one launch processes, over "
                  "that kernel's CUDA-event time. "}
     if top.startswith("tridiag"):
-        tri_bytes = 8.0 * B * sum((r - j - 1) * (r - j) / 2 for j in range(max(r - 2, 0)))
-        d["note"] += ("The kernel is not HBM bound at this size: it streams the trailing block of each r x r Gram matrix once "
-                      "per Householder step out of L2 (%.0f MB of Gram matrices per cube), %d dependent steps with four CTA "
-                      "barriers each; see roofline.stages.eigensolver for its modelled-flop rate against the measured FP32 "
-                      "peak. Minimal traffic of the algorithm itself (one read of the trailing lower triangle per step): "
-                      "%.2f GB per launch." % (B * r * r * 8 / 1e6, r - 2, tri_bytes / 1e9))
+        # what the algorithm itself must move: one read of the trailing lower triangle per Householder step, plus a
+        # read + write every eighth step (deferred rank-2 updates), tridiag_sym.cu
+        tri_bytes = 8.0 * B * sum((r - j - 1) * (r - j) / 2 for j in range(max(r - 2, 0))) * 1.25
+        flops = 16.0 / 3.0 * r ** 3 * B
+        d["note"] += ("The kernel is not HBM bound at this size: the %.0f MB of Gram matrices of a cube stay in L2 and the %d "
+                      "Householder steps of a matrix depend on each other; ncu (profiles/r02_ncu_full_c2_stages.txt): issue "
+                      "slots 53 %% busy with four warps per scheduler, DRAM at 0.3 %% - instruction and latency bound. Its "
+                      "own traffic (lower triangle once per step, L2): %.2f GB per launch; modelled flops 16/3 r^3 per "
+                      "matrix against the measured FP32 peak: roofline.stages.eigensolver." %
+                      (B * r * r * 8 / 1e6, r - 2, tri_bytes / 1e9))
         d["l2_algorithmic_gbs"] = tri_bytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else None
+        d["modelled_tflops"] = flops / (t_ms * 1e-3) / 1e12 if t_ms > 0 else None
     return d
 
 
@@ -510,6 +516,8 @@ def e2e_pipeline(Engine, torch, dist, dev, local, world, w, seconds=1.5):
     """e2e through the host-buffer C ABI: E2E_THREADS host threads, each with its own handle, stream and pinned buffers,
     each looping vk_compress_host -> vk_reconstruct_host on its own copy of the cube. Also one thread alone."""
     B, m, n, kw, kmax = w["B"], w["m"], w["n"], w["kw"], w["kmax"]
+    # measured on one GPU (KAT-7 cube): 2 threads 3.4, 3: 4.0, 4: 4.7, 6: 5.0, 8: 5.2 GVis/s (ceiling 5.9-6.0)
+    nthr = E2E_THREADS or max(2, min(6, len(os.sched_getaffinity(0)) // max(1, world)))
     per_mat = 8.0 * (2 * m * n + kmax * (m + n))
     Be = int(max(1, min(B, 6e9 // per_mat)))
 
@@ -517,7 +525,7 @@ def e2e_pipeline(Engine, torch, dist, dev, local, world, w, seconds=1.5):
         return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
 
     workers = []
-    for t in range(E2E_THREADS):
+    for t in range(nthr):
         eng = Engine(local)
         eng.host_stream = torch.cuda.Stream(device=dev)
         Ah = pinned((Be, m, n), torch.complex64)
@@ -567,17 +575,17 @@ def e2e_pipeline(Engine, torch, dist, dev, local, world, w, seconds=1.5):
 
     t1, n1 = timed(1, 3)
     per = max(2, int(seconds / max(t1 / n1, 1e-4) / 1.0))     # round trips per thread for ~seconds of pipelined running
-    tp, npipe = timed(E2E_THREADS, per)
+    tp, npipe = timed(nthr, per)
     fac_bytes = int(sum(x.nbytes for x in workers[0][2][:4]))
     vis = float(Be) * m * n * world
     res = {"value": vis * npipe / tp / 1e9, "unit": "GVis/s", "matrices_per_call_per_gpu": Be,
            "h2d_bytes_per_step": int((workers[0][1].nbytes + fac_bytes) * w["cps"]),
            "d2h_bytes_per_step": int((fac_bytes + workers[0][2][4].nbytes + workers[0][3].nbytes) * w["cps"]),
            "api": "vk_compress_host + vk_reconstruct_host (pinned host buffers, all copies inside the calls)",
-           "host_threads": E2E_THREADS, "round_trips_timed": npipe, "seconds": tp,
+           "host_threads": nthr, "round_trips_timed": npipe, "seconds": tp,
            "single_thread_value": vis * n1 / t1 / 1e9,
            "note": "one round trip = one cube up, factors down, factors up, cube down; %d host threads with a handle each "
-                   "(include/visco_b200.h: one handle per host thread) keep both PCIe directions and the GPU busy" % E2E_THREADS}
+                   "(include/visco_b200.h: one handle per host thread) keep both PCIe directions and the GPU busy" % nthr}
     for eng, *_ in workers:
         eng.close()
     return res
