@@ -15,9 +15,9 @@
 // CHUNK_KB K-blocks long into ping-pong TMEM accumulators that the converter warps promote into fp32 registers with
 // round-to-nearest adds (see gram_tc.cu for why).
 //
-// One CTA computes a 128 x 128 complex tile. Warp roles: warp 0 TMA producer (A operand: 3-D map, SWIZZLE_128B boxes of
-// 128 rows x 32 floats; B operand: 4-D map over (32 floats, contraction row, 32-float group, batch) so that the box
-// {32, 16, 8, 1} lands as 8 groups of 16 rows x 128 bytes), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11
+// One CTA computes a 128 x 128 complex tile. Warp roles: warp 0 TMA producer (A operand: 3-D map, SWIZZLE_64B boxes of
+// 128 rows x 16 floats; B operand: 4-D map over (32 floats, contraction row, 32-float group, batch) so that the box
+// {32, 8, 8, 1} lands as 8 groups of 8 rows x 128 bytes), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..11
 // converters (A: split in place; B: un-swizzle the raw row, optionally scale it by S[c], write rows 2k / 2k+1 of the
 // MN-major SWIZZLE_128B_BASE32B operand, hi and lo) and promoters / epilogue.
 #include "common.cuh"
@@ -28,20 +28,36 @@ using namespace tc;
 
 constexpr int TILE_M = 128;
 constexpr int TILE_NC = 128;              // complex output columns per tile = 256 floats = MMA N
-constexpr int KB_C = 16;                  // complex contraction elements per K-block (32 floats of A, 32 rows of B)
-constexpr int NSTAGE = 2;
-constexpr uint32_t A_BYTES = TILE_M * 128;        // 16 KiB  (128 rows x 32 floats)
-constexpr uint32_t BRAW_BYTES = 8 * KB_C * 128;   // 16 KiB  (8 groups x 16 rows x 128 B)
-constexpr uint32_t BCONV_BYTES = 8 * 2 * KB_C * 128;  // 32 KiB (8 groups x 32 rows x 128 B)
+// K-blocks of 8 complex contraction elements in a FOUR-stage ring: with blocks of 16 only two 112 KiB stages fit, and a
+// stage then goes TMA (1.5-2 us from L2 / HBM) -> conversion -> MMA strictly in turn - the tensor pipe was 38 % busy, the
+// converter warps mostly waiting for data (profiles/r02_ncu_full_c3_gram_cgemm.txt). Half-size blocks keep three loads in
+// flight behind the one being multiplied. The A operand rows are 16 floats = 64 bytes: SWIZZLE_64B.
+constexpr int KB_C = 8;                   // complex contraction elements per K-block (16 floats of A, 16 rows of B)
+constexpr int NSTAGE = 4;
+constexpr uint32_t A_BYTES = TILE_M * 2 * KB_C * 4;   // 8 KiB  (128 rows x 16 floats)
+constexpr uint32_t BRAW_BYTES = 8 * KB_C * 128;   // 8 KiB  (8 groups x 8 rows x 128 B)
+constexpr uint32_t BCONV_BYTES = 8 * 2 * KB_C * 128;  // 16 KiB (8 groups x 16 rows x 128 B)
 constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_RAW = 2 * A_BYTES, OFF_B_HI = 2 * A_BYTES + BRAW_BYTES,
                    OFF_B_LO = 2 * A_BYTES + BRAW_BYTES + BCONV_BYTES;
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + BRAW_BYTES + 2 * BCONV_BYTES;  // 112 KiB
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + BRAW_BYTES + 2 * BCONV_BYTES;  // 56 KiB
 constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + 128 + 1024;
+constexpr uint32_t SMEM_BYTES = OFF_BARS + 256 + 1024;
 constexpr int NUM_CONVERTERS = 256;
 constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int CHUNK_KB = 4;
+constexpr int CHUNK_KB = 8;               // K-blocks per TMEM accumulation chain (8 x 6 = 48 MMAs)
+constexpr int DRAIN_LAG = 3;              // a chunk is promoted this many K-blocks after its last block was converted
+
+// K-major SWIZZLE_64B operand: rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                    // layout type SWIZZLE_64B
+    return d;
+}
 
 enum { MODE_FORMV = 0, MODE_RECON = 1, MODE_PLAIN = 2 };
 
@@ -91,8 +107,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + OFF_BARS;
-    const uint32_t bar_raw = bars, bar_conv = bars + 16, bar_empty = bars + 32, bar_accf = bars + 48, bar_acce = bars + 64;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 96);
+    const uint32_t bar_raw = bars, bar_conv = bars + 8 * NSTAGE, bar_empty = bars + 16 * NSTAGE, bar_accf = bars + 24 * NSTAGE,
+                   bar_acce = bars + 24 * NSTAGE + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 24 * NSTAGE + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = g.tiles_m * g.tiles_n;
@@ -162,10 +179,10 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                const uint64_t a_hi = desc_kmajor_sw128(st + OFF_A_HI), a_lo = desc_kmajor_sw128(st + OFF_A_LO);
+                const uint64_t a_hi = desc_kmajor_sw64(st + OFF_A_HI), a_lo = desc_kmajor_sw64(st + OFF_A_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // 4 MMAs of K = 8 floats per K-block of 32
+                for (int k = 0; k < 2 * KB_C / 8; ++k) {  // MMAs of K = 8 floats per K-block of 2 KB_C
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);
                     // B: contraction rows 8k .. 8k+7 of every 32-float group: atom k of each group
                     const uint64_t b_hi = desc_mnmajor_sw128_32b(st + OFF_B_HI + k * 1024, 2 * KB_C * 128, 512);
@@ -206,8 +223,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 float4 av = a_hi[c];
                 if (MODE == MODE_RECON) {
                     // columns of U at or beyond ranks[b] are not part of the product, whatever they hold (the last K-block
-                    // may reach past the rank): logical 16-byte chunk = physical chunk XOR (row & 7) under SWIZZLE_128B
-                    const int col = kb * KB_C + 2 * ((c & 7) ^ ((c >> 3) & 7));
+                    // may reach past the rank): four 16-byte chunks per 64-byte row, logical chunk = physical chunk XOR
+                    // ((row >> 1) & 3) under SWIZZLE_64B
+                    const int col = kb * KB_C + 2 * ((c & 3) ^ ((c >> 3) & 3));
                     if (col >= Kvalid) av.x = av.y = 0.f;
                     if (col + 1 >= Kvalid) av.z = av.w = 0.f;
                 }
@@ -218,7 +236,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll 2
             for (int i = 0; i < (int)(BRAW_BYTES / 16) / NUM_CONVERTERS; ++i) {
                 const int c = ct + i * NUM_CONVERTERS;      // physical 16-byte chunk of the raw tile
-                const int grp = c >> 7;                      // 32-float group (16 rows x 8 chunks = 128 chunks each)
+                const int grp = c / (KB_C * 8);              // 32-float group (KB_C rows x 8 chunks each)
                 const int t = (c >> 3) & (KB_C - 1);         // contraction row inside the K-block
                 const int lc = (c & 7) ^ (t & 7);            // logical chunk: TMA swizzled it with the row index
                 float4 v = b_raw[c];
@@ -247,7 +265,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_conv + 8 * s);
-            if (kb >= CHUNK_KB + 1 && ((kb - 1) % CHUNK_KB) == 0)
+            if (kb >= CHUNK_KB + DRAIN_LAG && ((kb - DRAIN_LAG) % CHUNK_KB) == 0)
                 drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
         }
         while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
@@ -294,15 +312,15 @@ int make_map_a(vk_context* h, CUtensorMap* map, const float2* P, int rows, int k
     if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     const cuuint64_t dims[3] = {(cuuint64_t)2 * kc, (cuuint64_t)rows, (cuuint64_t)nb};
     const cuuint64_t strides[2] = {(cuuint64_t)2 * kc * 4, (cuuint64_t)rows * 2 * kc * 4};
-    const cuuint32_t box[3] = {32, TILE_M, 1};
+    const cuuint32_t box[3] = {2 * KB_C, TILE_M, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(P), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (A operand) failed: " + std::to_string((int)r));
     return VK_OK;
 }
-// B operand: Q[b][krows][nc] complex, N contiguous: view (32 floats, krows, 2*nc/32 groups, B); box {32, 16, 8, 1}
+// B operand: Q[b][krows][nc] complex, N contiguous: view (32 floats, krows, 2*nc/32 groups, B); box {32, KB_C, 8, 1}
 int make_map_b(vk_context* h, CUtensorMap* map, const float2* Q, int krows, int nc, int nb) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
