@@ -61,6 +61,14 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
 
 enum { MODE_FORMV = 0, MODE_RECON = 1, MODE_PLAIN = 2 };
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // (r0, i0, r1, i1) -> (-i0, r0, -i1, r1) : the row that multiplies the imaginary part of the A operand
 __device__ __forceinline__ float4 rot90(float4 v) { return make_float4(-v.y, v.x, -v.w, v.z); }
 
@@ -207,61 +215,73 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int j = 0; j < 128; ++j) acc[j] = 0.f;
         int next_drain = 0;
 
+        // what this thread converts is the same in every K-block: two 16-byte chunks of the A tile, two of the raw B tile
+        constexpr int NA = (int)(A_BYTES / 16) / NUM_CONVERTERS, NB = (int)(BRAW_BYTES / 16) / NUM_CONVERTERS;
+        int colA[NA], tB[NB];
+        uint32_t offA[NA], offBraw[NB], o0B[NB], o1B[NB];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int c = ct + i * NUM_CONVERTERS;
+            offA[i] = (uint32_t)c * 16;
+            // four 16-byte chunks per 64-byte row, logical chunk = physical chunk XOR ((row >> 1) & 3) under SWIZZLE_64B
+            colA[i] = 2 * ((c & 3) ^ ((c >> 3) & 3));
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int c = ct + i * NUM_CONVERTERS;      // physical 16-byte chunk of the raw tile
+            const int grp = c / (KB_C * 8);              // 32-float group (KB_C rows x 8 chunks each)
+            const int t = (c >> 3) & (KB_C - 1);         // contraction row inside the K-block
+            const int lc = (c & 7) ^ (t & 7);            // logical chunk: TMA swizzled it with the row index
+            const int r0 = 2 * t, r1 = 2 * t + 1;        // rows of the 2K x 2N real operand
+            tB[i] = t;
+            offBraw[i] = (uint32_t)c * 16;
+            // destination swizzle (BASE32B): 32-byte chunk index (lc >> 1) XOR (row & 3); 16-byte halves keep their order
+            o0B[i] = (uint32_t)(grp * 2 * KB_C + r0) * 128 + (uint32_t)(((((lc >> 1) ^ (r0 & 3)) << 1) | (lc & 1)) << 4);
+            o1B[i] = (uint32_t)(grp * 2 * KB_C + r1) * 128 + (uint32_t)(((((lc >> 1) ^ (r1 & 3)) << 1) | (lc & 1)) << 4);
+        }
+        const float* Sb = MODE == MODE_RECON ? g.S + (size_t)b * g.kmax : nullptr;
+
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % NSTAGE;
             const uint32_t use = kb / NSTAGE;
+            float sc[NB];
+            bool on[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {   // (the scale factors are on their way before the wait)
+                const int cc = kb * KB_C + tB[i];
+                on[i] = cc < Kvalid;
+                sc[i] = (MODE == MODE_RECON && on[i]) ? __ldg(Sb + cc) : 1.f;
+            }
             mbar_wait(bar_raw + 8 * s, use & 1);
-            unsigned char* st = smem + s * STAGE_BYTES;
-            float4* a_hi = reinterpret_cast<float4*>(st + OFF_A_HI);
-            float4* a_lo = reinterpret_cast<float4*>(st + OFF_A_LO);
-            const float4* b_raw = reinterpret_cast<const float4*>(st + OFF_B_RAW);
-            unsigned char* b_hi = st + OFF_B_HI;
-            unsigned char* b_lo = st + OFF_B_LO;
-#pragma unroll 2
-            for (int i = 0; i < (int)(A_BYTES / 16) / NUM_CONVERTERS; ++i) {
-                const int c = ct + i * NUM_CONVERTERS;
-                float4 av = a_hi[c];
+            const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                float4 av = lds128(st + OFF_A_HI + offA[i]);
                 if (MODE == MODE_RECON) {
                     // columns of U at or beyond ranks[b] are not part of the product, whatever they hold (the last K-block
-                    // may reach past the rank): four 16-byte chunks per 64-byte row, logical chunk = physical chunk XOR
-                    // ((row >> 1) & 3) under SWIZZLE_64B
-                    const int col = kb * KB_C + 2 * ((c & 3) ^ ((c >> 3) & 3));
+                    // may reach past the rank)
+                    const int col = kb * KB_C + colA[i];
                     if (col >= Kvalid) av.x = av.y = 0.f;
                     if (col + 1 >= Kvalid) av.z = av.w = 0.f;
                 }
                 const Split4 sa = split4(av);
-                a_hi[c] = sa.hi;
-                a_lo[c] = sa.lo;
+                sts128(st + OFF_A_HI + offA[i], sa.hi);
+                sts128(st + OFF_A_LO + offA[i], sa.lo);
             }
-#pragma unroll 2
-            for (int i = 0; i < (int)(BRAW_BYTES / 16) / NUM_CONVERTERS; ++i) {
-                const int c = ct + i * NUM_CONVERTERS;      // physical 16-byte chunk of the raw tile
-                const int grp = c / (KB_C * 8);              // 32-float group (KB_C rows x 8 chunks each)
-                const int t = (c >> 3) & (KB_C - 1);         // contraction row inside the K-block
-                const int lc = (c & 7) ^ (t & 7);            // logical chunk: TMA swizzled it with the row index
-                float4 v = b_raw[c];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                float4 v = lds128(st + OFF_B_RAW + offBraw[i]);
                 if (MODE == MODE_RECON) {
-                    const int cc = kb * KB_C + t;
-                    if (cc < Kvalid) {
-                        const float sc = g.S[(size_t)b * g.kmax + cc];
-                        v.x *= sc;
-                        v.y *= sc;
-                        v.z *= sc;
-                        v.w *= sc;
-                    } else {
-                        v = make_float4(0.f, 0.f, 0.f, 0.f);  // modes beyond ranks[b]: never read as data
-                    }
+                    // modes beyond ranks[b] are never read as data, whatever they hold
+                    v = on[i] ? make_float4(v.x * sc[i], v.y * sc[i], v.z * sc[i], v.w * sc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                // the (-qi, qr) twin row is the same numbers permuted and negated: so are its hi and lo parts (rounding to
+                // nearest is symmetric under negation)
                 const Split4 s0 = split4(v);
-                const Split4 s1 = split4(rot90(v));
-                const int r0 = 2 * t, r1 = 2 * t + 1;        // rows of the 2K x 2N real operand
-                // destination swizzle (BASE32B): 32-byte chunk index (lc >> 1) XOR (row & 3); 16-byte halves keep their order
-                const uint32_t o0 = (uint32_t)(grp * 2 * KB_C + r0) * 128 + (uint32_t)(((((lc >> 1) ^ (r0 & 3)) << 1) | (lc & 1)) << 4);
-                const uint32_t o1 = (uint32_t)(grp * 2 * KB_C + r1) * 128 + (uint32_t)(((((lc >> 1) ^ (r1 & 3)) << 1) | (lc & 1)) << 4);
-                *reinterpret_cast<float4*>(b_hi + o0) = s0.hi;
-                *reinterpret_cast<float4*>(b_lo + o0) = s0.lo;
-                *reinterpret_cast<float4*>(b_hi + o1) = s1.hi;
-                *reinterpret_cast<float4*>(b_lo + o1) = s1.lo;
+                sts128(st + OFF_B_HI + o0B[i], s0.hi);
+                sts128(st + OFF_B_LO + o0B[i], s0.lo);
+                sts128(st + OFF_B_HI + o1B[i], rot90(s0.hi));
+                sts128(st + OFF_B_LO + o1B[i], rot90(s0.lo));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_conv + 8 * s);
