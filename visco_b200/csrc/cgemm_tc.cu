@@ -48,27 +48,8 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr int CHUNK_KB = 8;               // K-blocks per TMEM accumulation chain (8 x 6 = 48 MMAs)
 constexpr int DRAIN_LAG = 3;              // a chunk is promoted this many K-blocks after its last block was converted
 
-// K-major SWIZZLE_64B operand: rows of 64 bytes, 8-row groups 512 bytes apart
-__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;                    // layout type SWIZZLE_64B
-    return d;
-}
-
 enum { MODE_FORMV = 0, MODE_RECON = 1, MODE_PLAIN = 2 };
 
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 // (r0, i0, r1, i1) -> (-i0, r0, -i1, r1) : the row that multiplies the imaginary part of the A operand
 __device__ __forceinline__ float4 rot90(float4 v) { return make_float4(-v.y, v.x, -v.w, v.z); }
 

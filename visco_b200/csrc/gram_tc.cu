@@ -15,7 +15,7 @@
 // into fp32 registers with round-to-nearest adds while the tensor core fills the other buffer.
 //
 // Kernel: one CTA per upper-triangular 128 x 128 tile pair (I <= J) of one matrix; the mirrored tile is written as the
-// conjugate transpose. Warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes of 128 rows x 32
+// conjugate transpose. Warp roles: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_64B boxes of 128 rows x 16
 // floats), warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4..11 = converters (split raw fp32 tiles into
 // hi/lo and the swapped copy, in place, swizzle-agnostic because the split is element-wise within 16-byte chunks)
 // and promoters (tcgen05.ld of finished chunks -> register accumulators -> global at the end). The converter warps
@@ -27,19 +27,22 @@ namespace {
 using namespace tc;
 
 constexpr int TILE = 128;             // rows of a tile (both I and J)
-constexpr int KB_FLOATS = 32;         // K-block: 32 floats = 128 bytes = one SWIZZLE_128B row
-constexpr int NSTAGE = 2;
-constexpr uint32_t A_TILE_BYTES = TILE * 128;          // 16 KiB
-constexpr uint32_t B_TILE_BYTES = 2 * TILE * 128;      // 32 KiB (R_J rows then Q_J rows)
+// K-blocks of 16 floats (one SWIZZLE_64B row) in a four-stage ring: three loads stay in flight behind the block being
+// multiplied (with 32-float blocks only two 96 KiB stages fit, and a stage goes load -> split -> MMA strictly in turn)
+constexpr int KB_FLOATS = 16;
+constexpr int NSTAGE = 4;
+constexpr uint32_t A_TILE_BYTES = TILE * KB_FLOATS * 4;          // 8 KiB
+constexpr uint32_t B_TILE_BYTES = 2 * TILE * KB_FLOATS * 4;      // 16 KiB (R_J rows then Q_J rows)
 constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_TILE_BYTES, OFF_B_HI = 2 * A_TILE_BYTES,
                    OFF_B_LO = 2 * A_TILE_BYTES + B_TILE_BYTES;
-constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 96 KiB
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 48 KiB
 constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BARS + 128 + 1024;  // + barriers + alignment slack
+constexpr uint32_t SMEM_BYTES = OFF_BARS + 256 + 1024;  // + barriers + alignment slack
 constexpr int NUM_CONVERTERS = 256;
 constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
 constexpr uint32_t TMEM_COLS = 512;  // two 256-column accumulators (re | im), ping-pong
-constexpr int CHUNK_KB = 4;           // K-blocks per TMEM accumulation chain (4 x 12 = 48 MMAs)
+constexpr int CHUNK_KB = 8;           // K-blocks per TMEM accumulation chain (8 x 6 = 48 MMAs)
+constexpr int DRAIN_LAG = 3;          // a chunk is promoted this many K-blocks after its last block was converted
 
 // (r0, i0, r1, i1) -> (i0, -r0, i1, -r1)
 __device__ __forceinline__ float4 swap_neg(float4 v) { return make_float4(v.y, -v.x, v.w, -v.z); }
@@ -71,15 +74,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W, int m, int n2, int tiles_per_mat,
                int T) {
     extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte alignment
+    // swizzled operands need 1024-byte alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + OFF_BARS;
     // barrier slots (8 bytes each): raw_full[s] @0,8 ; conv_full[s] @16,24 ; empty[s] @32,40 ; acc_full[p] @48,56 ;
     // acc_empty[p] @64,72 ; tmem ptr @96
-    const uint32_t bar_raw = bars, bar_conv = bars + 16, bar_empty = bars + 32, bar_accf = bars + 48,
-                   bar_acce = bars + 64;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 96);
+    const uint32_t bar_raw = bars, bar_conv = bars + 8 * NSTAGE, bar_empty = bars + 16 * NSTAGE, bar_accf = bars + 24 * NSTAGE,
+                   bar_acce = bars + 24 * NSTAGE + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 24 * NSTAGE + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x / tiles_per_mat;
@@ -153,9 +156,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = sbase + s * STAGE_BYTES;
-                const uint64_t a_hi = desc_kmajor_sw128(st + (diag ? OFF_B_HI : OFF_A_HI)),
-                               a_lo = desc_kmajor_sw128(st + (diag ? OFF_B_LO : OFF_A_LO));
-                const uint64_t b_hi = desc_kmajor_sw128(st + OFF_B_HI), b_lo = desc_kmajor_sw128(st + OFF_B_LO);
+                const uint64_t a_hi = desc_kmajor_sw64(st + (diag ? OFF_B_HI : OFF_A_HI)),
+                               a_lo = desc_kmajor_sw64(st + (diag ? OFF_B_LO : OFF_A_LO));
+                const uint64_t b_hi = desc_kmajor_sw64(st + OFF_B_HI), b_lo = desc_kmajor_sw64(st + OFF_B_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
                 for (int k = 0; k < KB_FLOATS / 8; ++k) {
@@ -184,32 +187,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
             const int s = kb % NSTAGE;
             const uint32_t use = kb / NSTAGE;
             mbar_wait(bar_raw + 8 * s, use & 1);
-            unsigned char* st = smem + s * STAGE_BYTES;
-            float4* a_hi = reinterpret_cast<float4*>(st + OFF_A_HI);
-            float4* a_lo = reinterpret_cast<float4*>(st + OFF_A_LO);
-            float4* b_hi = reinterpret_cast<float4*>(st + OFF_B_HI);
-            float4* b_lo = reinterpret_cast<float4*>(st + OFF_B_LO);
-            constexpr int CH = A_TILE_BYTES / 16;  // 1024 chunks per 128-row tile
-#pragma unroll 2
+            const uint32_t st = sbase + s * STAGE_BYTES;
+            constexpr int CH = A_TILE_BYTES / 16;  // 512 chunks per 128-row tile
+#pragma unroll
             for (int i = 0; i < CH / NUM_CONVERTERS; ++i) {
-                const int c = ct + i * NUM_CONVERTERS;
+                const uint32_t o = (uint32_t)(ct + i * NUM_CONVERTERS) * 16;
                 if (!diag) {
-                    const Split4 sa = split4(a_hi[c]);
-                    a_hi[c] = sa.hi;
-                    a_lo[c] = sa.lo;
+                    const Split4 sa = split4(lds128(st + OFF_A_HI + o));
+                    sts128(st + OFF_A_HI + o, sa.hi);
+                    sts128(st + OFF_A_LO + o, sa.lo);
                 }
-                const Split4 sb = split4(b_hi[c]);
-                b_hi[c] = sb.hi;
-                b_lo[c] = sb.lo;
-                b_hi[c + CH] = swap_neg(sb.hi);
-                b_lo[c + CH] = swap_neg(sb.lo);
+                const Split4 sb = split4(lds128(st + OFF_B_HI + o));
+                sts128(st + OFF_B_HI + o, sb.hi);
+                sts128(st + OFF_B_LO + o, sb.lo);
+                sts128(st + OFF_B_HI + A_TILE_BYTES + o, swap_neg(sb.hi));
+                sts128(st + OFF_B_LO + A_TILE_BYTES + o, swap_neg(sb.lo));
             }
             // make the generic-proxy writes visible to the tensor core (async proxy), then signal
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_conv + 8 * s);
-            // promote a finished chunk two K-blocks after its last block was converted: its MMAs have retired by
-            // then (the pipeline is NSTAGE = 2 deep), so this wait does not stall the conversion stream
-            if (kb >= CHUNK_KB + 1 && ((kb - 1) % CHUNK_KB) == 0) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc_re, acc_im);
+            // promote a finished chunk DRAIN_LAG K-blocks after its last block was converted: its MMAs have mostly retired
+            // by then, so this wait does not stall the conversion stream
+            if (kb >= CHUNK_KB + DRAIN_LAG && ((kb - DRAIN_LAG) % CHUNK_KB) == 0) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc_re, acc_im);
         }
         while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc_re, acc_im);
 
@@ -264,7 +263,7 @@ int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                                   const_cast<float2*>(A + (size_t)b0 * m * n), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
             return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));

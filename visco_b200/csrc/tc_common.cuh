@@ -54,6 +54,24 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B
     return d;
 }
+// K-major SWIZZLE_64B operand: rows of 64 bytes (16 tf32), 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                    // layout type SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // MN-major operand. For 32-bit (tf32) MN-major data the only layout the tensor core accepts is SWIZZLE_128B_BASE32B
 // (cute::UMMA::Layout_MN_SW128_32B_Atom, layout type 1): 32 MN elements (128 bytes) contiguous per contraction row, atoms
 // of FOUR contraction rows (512 bytes), and inside an atom the 32-byte chunk index is XOR-ed with the row index
