@@ -106,7 +106,13 @@ int gram_chunk(const vk_context* h, int B, int chunk, int m, int n) {
 int ensure(vk_context* h, void** p, size_t* have, size_t need) {
     if (*have >= need) return VK_OK;
     if (*p) {
+        // every stream of this handle may still reference the old block: the Jacobi driver's group streams and the copy
+        // streams of the *_host entry points as well as the main stream
         cudaStreamSynchronize(h->stream);
+        for (int i = 0; i < VK_MAX_GROUPS; ++i)
+            if (h->sub[i]) cudaStreamSynchronize(h->sub[i]);
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        if (h->copy_stream2) cudaStreamSynchronize(h->copy_stream2);
         cudaFree(*p);
         *p = nullptr;
         *have = 0;
@@ -139,10 +145,12 @@ int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, f
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
     int rc;
-    const bool tc = (h->gram_impl == 2) || (h->gram_impl == 0 && vk_gram_tc_supported(m, n, side));
+    // (tensor maps need a 16-byte aligned base: a misaligned device pointer takes the SIMT kernels)
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(A) % 16) == 0;
+    const bool tc = (h->gram_impl == 2) || (h->gram_impl == 0 && vk_gram_tc_supported(m, n, side) && aligned16);
     if (tc) {
-        if (!vk_gram_tc_supported(m, n, side))
-            return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape");
+        if (!vk_gram_tc_supported(m, n, side) || !aligned16)
+            return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape or alignment");
         if ((rc = vk_launch_gram_tc(h, A, B, m, n, W))) return rc;
     } else {
         if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;

@@ -1030,7 +1030,8 @@ int vk_launch_factors_gram(vk_context* h, const float2* A, const float2* W, int 
         FormVOp op{A, W, perm_dev, inv_dev, ranks_dev, Vt, norm2_dev, m, n, kmax};
         const bool aligned = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Vt)) % 16 == 0);
         // (the K-major operand X has rows of m complex numbers: its tensor map needs 16-byte strides, i.e. an even m)
-        if (xbuf && h->gemm_impl == 0 && kmax > 16 && (m % 2) == 0 && vk_cgemm_tc_supported(m, n, kmax)) {
+        if (xbuf && h->gemm_impl == 0 && kmax > 16 && (m % 2) == 0 && vk_cgemm_tc_supported(m, n, kmax) && aligned &&
+            (reinterpret_cast<uintptr_t>(xbuf) % 16) == 0) {
             // large rank: X = conj(U_k)^T / lambda materialised K-major, then the tcgen05 complex GEMM
             if ((rc = launch_rows(h, W, r, r, 0, m, kmax, perm_dev, inv_dev, ranks_dev, 1, 1, xbuf, B))) return rc;
             rc = vk_launch_formv_tc(h, xbuf, A, ranks_dev, Vt, norm2_dev, B, m, n, kmax);

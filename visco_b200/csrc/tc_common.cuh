@@ -143,14 +143,16 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
 inline PFN_encodeTiled get_encode_tiled() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
+    // (function-local static with an initialiser: initialised once, thread-safe by the language rules - handles of
+    // different host threads may get here at the same time)
+    static const PFN_encodeTiled fn = []() -> PFN_encodeTiled {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
+            return reinterpret_cast<PFN_encodeTiled>(p);
+        return nullptr;
+    }();
     return fn;
 }
 
