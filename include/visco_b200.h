@@ -42,7 +42,7 @@ extern "C" {
 #define VK_EINVAL 1  /* bad argument (shape, NULL pointer, kmax too small, ...)  -> Python ValueError      */
 #define VK_ENOMEM 2  /* device or host allocation failed                         -> Python MemoryError     */
 #define VK_ECUDA 3   /* a CUDA call or kernel failed                             -> Python RuntimeError    */
-#define VK_ENOCONV 4 /* Jacobi did not converge within max_sweeps (numpy raises LinAlgError here)          */
+#define VK_ENOCONV 4 /* the eigensolver did not converge for some matrix (numpy raises LinAlgError here)        */
 #define VK_ENONFINITE 5 /* NaN/Inf in the input (flagged rows NaN-masked by ds.where, compress_ms.py:470)  */
 
 typedef struct vk_context* vk_handle;

@@ -619,7 +619,7 @@ int vk_compress_host(vk_handle h, const void* A, int B, int m, int n, int fixed_
     VK_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int b = 0; b < B; ++b)
         if (stats[4 * b + 3] == 0.f)
-            return vk_fail(h, VK_ENOCONV, "Jacobi did not converge for matrix " + std::to_string(b));
+            return vk_fail(h, VK_ENOCONV, "the eigensolver did not converge for matrix " + std::to_string(b));
     return VK_OK;
 }
 
