@@ -206,3 +206,59 @@ def test_full_spectrum_paths_agree(eng, torch, shape, dec):
         if b in (0, 1, 5):
             parity.check_factors(Ah[b], res[0][0][b, :, :k0], res[0][1][b, :k0], res[0][2][b, :k0], k0, decorrelation=dec,
                                  label=f"eigvec {shape} dec{dec} b={b}")
+
+
+# ------------------------------------------------------------------------------------------------ round-2 kernels
+@pytest.mark.parametrize("B,m,n,kw,opts", [
+    (304, 200, 600, dict(compressionrank=5), {}),                # tridiag_sym.cu: ragged r, more matrices than SMs (two per SM)
+    (12, 200, 600, dict(decorrelation=0.97), {}),                # ... ragged r, one matrix per SM, full spectrum through QL (r % 16)
+    (8, 384, 1000, dict(decorrelation=0.98), {}),                # ... r = 384 (12 column chunks), full-spectrum path
+    (6, 144, 400, dict(compressionrank=12), {}),                 # ... smallest sizes of that kernel
+    (6, 512, 1024, dict(compressionrank=3), {"tridiag_variant": 2}),   # two-per-SM launch shape forced on a small batch
+    (6, 256, 1024, dict(compressionrank=8), {"tridiag_impl": 1}),      # round 1's undeferred kernels stay selectable
+    (10, 16, 4096, dict(compressionrank=4), {}),                 # tridiag_small.cu, one warp per matrix (r <= 33, too long for the Jacobi path)
+    (10, 33, 3000, dict(decorrelation=0.9), {}),                 # ... odd r, full path
+    (10, 64, 4096, dict(compressionrank=8), {}),                 # ... two warps per matrix
+    (10, 50, 60, dict(decorrelation=0.95), {}),                  # 32 < r <= 64, Gram route by default
+])
+def test_round2_tridiagonalisation_kernels(eng, torch, B, m, n, kw, opts):
+    A = _device_cube(eng, torch, B, 1, m, n)
+    for k_, v_ in opts.items():
+        eng.set_option(k_, v_)
+    try:
+        U, S, Vt, ranks, stats = eng.compress(A, **kw)
+    finally:
+        for k_ in opts:
+            eng.set_option(k_, 0)
+    torch.cuda.synchronize()
+    Ah, Uh, Sh, Vh, rk, st = (x.cpu().numpy() for x in (A, U, S, Vt, ranks, stats))
+    assert np.all(st[:, 3] == 1)
+    for b in sorted(set(range(0, B, max(1, B // 6))) | {B - 1}):
+        k = int(rk[b])
+        parity.check_factors(Ah[b], Uh[b, :, :k], Sh[b, :k], Vh[b, :k], k, label=f"r2 {m}x{n} {kw} {opts} b={b}", **kw)
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 1024, 8), (200, 1000, 3), (128, 2048, 16), (96, 250, 5), (300, 2050, 7), (256, 1024, 1)])
+def test_fused_factor_formation_matches_the_separate_kernels(eng, torch, m, n, k):
+    """factors_fused_kernel (one cluster launch: U, refined sigma, normalised Vt, retained energy) against the five-launch
+    path it replaces ("factors_impl" = 1) and against the oracle; ragged last strip (n % 256 != 0), k below the template
+    width, n beyond eight strips (falls back to the separate kernels)."""
+    A = _device_cube(eng, torch, 9, 1, m, n)
+    res = {}
+    for impl in (1, 0):
+        eng.set_option("factors_impl", impl)
+        try:
+            res[impl] = [x.clone() for x in eng.compress(A, compressionrank=k)]
+        finally:
+            eng.set_option("factors_impl", 0)
+    torch.cuda.synchronize()
+    U0, S0, V0, r0, t0 = (x.cpu().numpy() for x in res[0])
+    U1, S1, V1, r1, t1 = (x.cpu().numpy() for x in res[1])
+    np.testing.assert_array_equal(r0, r1)
+    np.testing.assert_array_equal(U0, U1)                          # same gather
+    np.testing.assert_allclose(S0, S1, rtol=2e-6)                 # summation order differs (atomics vs fixed order)
+    np.testing.assert_allclose(t0[:, 1], t1[:, 1], rtol=1e-5)
+    assert np.abs(V0 - V1).max() <= 2e-6 * np.abs(V1).max()
+    Ah = A.cpu().numpy()
+    for b in (0, 8):
+        parity.check_factors(Ah[b], U0[b], S0[b], V0[b], k, compressionrank=k, label=f"fused factors {m}x{n} k{k} b={b}")
