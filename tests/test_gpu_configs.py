@@ -262,3 +262,30 @@ def test_fused_factor_formation_matches_the_separate_kernels(eng, torch, m, n, k
     Ah = A.cpu().numpy()
     for b in (0, 8):
         parity.check_factors(Ah[b], U0[b], S0[b], V0[b], k, compressionrank=k, label=f"fused factors {m}x{n} k{k} b={b}")
+
+
+def test_remainder_split_of_the_eigensolver_changes_nothing(eng, torch):
+    """More matrices than SMs with a small remainder: the remainder runs as its own sub-batch on a second stream
+    (tridiag.cu, "tail_split"). The split also switches the main sub-batch to the one-matrix-per-SM launch shape (other
+    tile height and deferral depth), so the two runs agree to rounding, not bit for bit; both are checked against the
+    oracle."""
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    B, m, n = nsm + 5, 160, 512
+    A = _device_cube(eng, torch, B, 1, m, n)
+    res = {}
+    for off in (1, 0):
+        eng.set_option("tail_split", off)
+        try:
+            res[off] = [x.clone() for x in eng.compress(A, decorrelation=0.97)]
+        finally:
+            eng.set_option("tail_split", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][3], res[1][3])                                     # ranks
+    assert float(((res[0][1] - res[1][1]).abs() / res[1][1].abs().clamp_min(1e-20)).max()) < 2e-5
+    Ah = A.cpu().numpy()
+    for off in (0, 1):
+        U, S, Vt, ranks, stats = (x.cpu().numpy() for x in res[off])
+        assert np.all(stats[:, 3] == 1)
+        for b in (0, nsm - 1, nsm, B - 1):
+            k = int(ranks[b])
+            parity.check_factors(Ah[b], U[b, :, :k], S[b, :k], Vt[b, :k], k, decorrelation=0.97, label=f"tail split {off} b={b}")

@@ -113,6 +113,7 @@ int ensure(vk_context* h, void** p, size_t* have, size_t need) {
             if (h->sub[i]) cudaStreamSynchronize(h->sub[i]);
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
         if (h->copy_stream2) cudaStreamSynchronize(h->copy_stream2);
+        if (h->tail_stream) cudaStreamSynchronize(h->tail_stream);
         cudaFree(*p);
         *p = nullptr;
         *have = 0;
@@ -372,6 +373,9 @@ int vk_destroy(vk_handle h) {
     for (auto& e : h->sub_ev)
         if (e) cudaEventDestroy(e);
     if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
+    for (int i = 0; i < 2; ++i)
+        if (h->tail_ev[i]) cudaEventDestroy(h->tail_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
     for (auto& e : h->host_ev)
@@ -430,6 +434,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "tridiag_impl")
         h->tridiag_impl = (int)v;
+    else if (k == "tail_split")
+        h->tail_split = (int)v;
     else if (k == "factors_impl")
         h->factors_impl = (int)v;
     else if (k == "small_impl")

@@ -44,6 +44,10 @@ struct vk_context {
     int tridiag_variant = 0;  // tridiag_sym.cu: 0 = by batch size, 1 = one matrix per SM, 2 = two per SM
     int small_impl = 0;       // one-sided Jacobi path: 0 = for r <= 32, 1 = whenever the matrix fits one CTA, 2 = never
     int factors_impl = 0;     // small ranks on the wide Gram path: 0 = one fused cluster kernel, 1 = the separate kernels
+    int tail_split = 0;       // direct eigensolver: 0 = remainder sub-batch on a second stream (tridiag.cu), 1 = off
+    bool in_split = false;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t tail_ev[2] = {nullptr, nullptr};
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems

@@ -1887,7 +1887,8 @@ int topk_qr_limit(int r) {
 
 bool vk_eigqr_supported(int r) { return r >= 2 && r <= 1024; }
 
-size_t vk_eigqr_scratch_bytes(int B, int r) { return eig_layout(B, r).total; }
+// (+ slack: the remainder split below lays two sub-batches out one after the other)
+size_t vk_eigqr_scratch_bytes(int B, int r) { return eig_layout(B, r).total + (64u << 10); }
 
 // W [B][r][ld] in/out (see the header comment); scratch: vk_eigqr_scratch_bytes(B, r) bytes of device memory.
 // done_dev[b] = 1 / sweeps_dev[b] = QL iterations on success; done_dev[b] = 0 when the rotation store overflowed or
@@ -1898,6 +1899,38 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
                     int32_t* done_dev, int fixed_rank, double decorrelation) {
     if (B <= 0) return VK_OK;
     if (!vk_eigqr_supported(r)) return vk_fail(h, VK_EINVAL, "eig_impl=2 does not support this size");
+    // Remainder split ("tail_split" 0 = on): the tridiagonalisation runs one matrix per SM, so B = q * SMs + rem matrices take
+    // q + 1 waves and the last one holds only rem matrices (the MeerKAT shard: 1040 = 7 x 148 + 4, 12 % of the kernel). The
+    // remainder is a sub-batch of its own on a second stream that starts when the main sub-batch has left the
+    // tridiagonalisation: its few CTAs run under the main sub-batch's later stages. Same arithmetic per matrix either way.
+    {
+        const int nsm = h->num_sms, rem = B % nsm;
+        if (h->tail_split == 0 && !h->in_split && h->stage_timing == 0 && h->tridiag_impl == 0 && vk_tridiag_symdefer_supported(r) &&
+            B > nsm && rem > 0 && rem * 4 <= nsm) {
+            const int B1 = B - rem;
+            if (!h->tail_stream) VK_CUDA(h, cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i)
+                if (!h->tail_ev[i]) VK_CUDA(h, cudaEventCreateWithFlags(&h->tail_ev[i], cudaEventDisableTiming));
+            cudaStream_t main_st = h->stream;
+            const int save_variant = h->tridiag_variant;
+            h->in_split = true;
+            h->tridiag_variant = 1;   // one matrix per SM: B1 is a whole number of waves
+            int rc = vk_launch_eigqr(h, W, B1, r, ld, scratch, sweeps_dev, done_dev, fixed_rank, decorrelation);
+            if (!rc) {
+                unsigned char* sc2 = static_cast<unsigned char*>(scratch) + al(eig_layout(B1, r).total);
+                cudaStreamWaitEvent(h->tail_stream, h->tail_ev[0], 0);   // recorded behind the main sub-batch's tridiagonalisation
+                h->stream = h->tail_stream;
+                rc = vk_launch_eigqr(h, W + (size_t)B1 * r * ld, rem, r, ld, sc2, sweeps_dev + B1, done_dev + B1, fixed_rank,
+                                     decorrelation);
+                h->stream = main_st;
+                cudaEventRecord(h->tail_ev[1], h->tail_stream);
+                cudaStreamWaitEvent(main_st, h->tail_ev[1], 0);
+            }
+            h->tridiag_variant = save_variant;
+            h->in_split = false;
+            return rc;
+        }
+    }
     const EigScratch L = eig_layout(B, r);
     unsigned char* sc = static_cast<unsigned char*>(scratch);
     cudaStream_t st = h->stream;
@@ -1932,6 +1965,7 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
     else if (r <= 512) rc = launch_tridiag<16, 2>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     else rc = launch_tridiag<32, 1>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     if (rc) return rc;
+    if (h->in_split && st != h->tail_stream) cudaEventRecord(h->tail_ev[0], st);   // the remainder sub-batch may start
     if (dbg) cudaEventRecord(ev[1], st);
     const int32_t* skip = nullptr;
     // sweeps in flight in the rotation application (and in the level assignment of the QL kernel): measured 1.85 vs 2.31 ms
