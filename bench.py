@@ -54,7 +54,7 @@ NCUBES = {"kat7": 4, "meerkat": 1, "small": 4, "small_jacobi": 4}
 OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload runs with (reset afterwards)
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
 # (one CTA per matrix: 112 of 148 SMs at the KAT-7 shape, host polls in between) overlaps the other stages of the next
-HANDLES = {"kat7": 2, "meerkat": 1, "small": 2, "small_jacobi": 2}
+HANDLES = {"kat7": 3, "meerkat": 1, "small": 3, "small_jacobi": 3}
 E2E_THREADS = int(os.environ.get("VISCO_E2E_THREADS", "0"))   # 0: six, or as many as the rank's share of the host cores allows
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
 
@@ -338,11 +338,13 @@ def run_workload(eng, Engine, torch, dist, dev, world, rank, name, steps, warmup
             dist.barrier()
         torch.cuda.synchronize()
 
-    nh = HANDLES[name]
+    nh = int(os.environ.get("VISCO_BENCH_HANDLES", HANDLES[name]))
     engines = [eng] + [Engine(eng.device) for _ in range(nh - 1)]
     for e_ in engines:
         for k_, v_ in OPTIONS.get(name, {}).items():
             e_.set_option(k_, v_)
+        for kv in filter(None, os.environ.get("VISCO_BENCH_OPTIONS", "").split(",")):   # development: "name=value,..."
+            e_.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     streams = [torch.cuda.Stream(device=dev) for _ in range(nh)]
     facs = [fac] + [tuple(torch.empty_like(x) for x in fac) for _ in range(nh - 1)]
     outs = [out] + [torch.empty_like(out) for _ in range(nh - 1)]

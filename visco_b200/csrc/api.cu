@@ -1,12 +1,28 @@
 // C ABI of libvisco_b200.so (see include/visco_b200.h). Orchestrates the stages; no arithmetic here.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "common.cuh"
 
+// host threads currently inside vk_compress_batched, per device: with several handles feeding one GPU the kernels that
+// would take a whole SM per matrix choose the launch shape that lets two of them share one (tridiag_sym.cu)
+static std::atomic<int> g_in_compress[64];
+int vk_concurrent_compress(int device) { return (device >= 0 && device < 64) ? g_in_compress[device].load(std::memory_order_relaxed) : 1; }
+
 namespace {
+
+struct InCompress {
+    int d;
+    explicit InCompress(int dev) : d(dev) {
+        if (d >= 0 && d < 64) g_in_compress[d].fetch_add(1, std::memory_order_relaxed);
+    }
+    ~InCompress() {
+        if (d >= 0 && d < 64) g_in_compress[d].fetch_sub(1, std::memory_order_relaxed);
+    }
+};
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -486,6 +502,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     if (decorrelation < 0.0 || !(decorrelation == decorrelation))
         return vk_fail(h, VK_EINVAL, "decorrelation must be >= 0");
     VK_CUDA(h, cudaSetDevice(h->device));
+    InCompress in_compress(h->device);
     const bool qr = use_qr(h, m, n, fixed_rank);
     int chunk = h->chunk > 0 ? h->chunk : auto_chunk(h, B, m, n, qr);
     if (chunk > B) chunk = B;

@@ -132,6 +132,7 @@ bool vk_eigqr_supported(int r);
 size_t vk_eigqr_scratch_bytes(int B, int r);
 int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratch, int32_t* sweeps_dev,
                     int32_t* done_dev, int fixed_rank = 0, double decorrelation = 0.0);
+int vk_concurrent_compress(int device);   // host threads inside vk_compress_batched on this device (api.cu)
 // lower-triangle, deferred-update Householder tridiagonalisation (tridiag_sym.cu); outputs as the kernels of tridiag.cu
 bool vk_tridiag_symdefer_supported(int r);
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,

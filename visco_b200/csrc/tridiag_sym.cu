@@ -497,8 +497,10 @@ bool vk_tridiag_symdefer_supported(int r) { return r > 128 && r <= 512; }
 
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,
                                float* e, float* tau, float2* ph) {
-    // two matrices per SM once there are more matrices than SMs ("tridiag_variant": 1 / 2 force one / two per SM)
-    int variant = B > h->num_sms ? 1 : 0;
+    // two matrices per SM once there are more matrices than SMs, or when three or more host threads are feeding this GPU
+    // through their own handles (KAT-7 cube, 112 matrices: alone 1.58 vs 2.05 ms, but three concurrent handles reach 1.57
+    // instead of 1.67 ms per cube because the cubes' kernels can share SMs); "tridiag_variant": 1 / 2 force one / two per SM
+    int variant = (B > h->num_sms || vk_concurrent_compress(h->device) >= 3) ? 1 : 0;
     if (h->tridiag_variant == 1) variant = 0;
     if (h->tridiag_variant == 2) variant = 1;
     if (r <= 256) return launch_symdefer_r<8>(h, st, W, B, r, ld, wstride, d, e, tau, ph, variant);
