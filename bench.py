@@ -49,7 +49,7 @@ WORKLOADS = {
     "small_jacobi": (2080, 4, 64, 64, dict(compressionrank=8), "configs[3]: 2080 bl x 4 corr x 64 x 64, one-sided Jacobi path "
                      "as the configuration names it (option small_impl = 1)"),
 }
-CUBES_PER_STEP = {"kat7": 32, "meerkat": 1, "small": 8, "small_jacobi": 8}
+CUBES_PER_STEP = {"kat7": 64, "meerkat": 1, "small": 8, "small_jacobi": 8}   # kat7: one step = 0.1 s, 20 steps = 2 s of steady load
 NCUBES = {"kat7": 4, "meerkat": 1, "small": 4, "small_jacobi": 4}
 OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload runs with (reset afterwards)
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
