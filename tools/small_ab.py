@@ -8,8 +8,8 @@ B, m, n, k = 8320, 64, 64, 8
 A = torch.empty((B, m, n), dtype=torch.complex64, device="cuda:0")
 eng.synth_fill(A, B // 4, 4)
 ref = None
-for off in (0, 1, 1, 0):
-    eng.set_option("small_off", off)
+for off in (0, 1, 1, 0):                   # 0: one-sided Jacobi route (small_impl = 1), 1: default route
+    eng.set_option("small_impl", 0 if off else 1)
     eng.set_option("stage_timing", 2 if off else 0)
     for _ in range(2):
         torch.cuda.synchronize()
