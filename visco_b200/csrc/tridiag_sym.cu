@@ -79,11 +79,14 @@ struct TileIt {
 
 // NT threads per CTA (512: one CTA per SM, the whole SM on one matrix - few matrices; 256: two CTAs, i.e. two matrices, per
 // SM so that one's barriers and scalar phases hide behind the other's pass - many matrices); DB: register double buffer
-template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED>
+// LDC: the row stride when it is known at compile time (0: use ld) - the eight loads of a tile then share one base
+// register pair and immediate offsets instead of a 64-bit add each
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
-    tridiag_symdefer_kernel(float2* __restrict__ Wall, int r, int ld, size_t wstride, float* __restrict__ dall,
+    tridiag_symdefer_kernel(float2* __restrict__ Wall, int r, int ld_, size_t wstride, float* __restrict__ dall,
                             float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
     constexpr int WD = EPL * 32;
+    const int ld = LDC ? LDC : ld_;
     constexpr int SD_THREADS = NT, SD_WARPS = NT / 32;
     static_assert(NB <= SD_WARPS, "one warp per pending pair computes its two inner products");
     static_assert(TR == 8 || TR == 16, "row block height");
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 #pragma unroll
                 for (int rr = 0; rr < TR; ++rr) {
                     if (RAGGED) x[rr] = (t.I * TR + rr < r && k < r) ? src[(size_t)rr * ld] : make_float2(0.f, 0.f);
+                    else if (LDC) x[rr] = src[rr * LDC];
                     else x[rr] = src[(size_t)rr * ld];
                 }
             };
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     for (int rr = 0; rr < TR; ++rr) {
                         bool ok = !last || k <= i0 + rr;
                         if (RAGGED) ok = ok && (i0 + rr < r) && (k < r);
-                        if (ok) dst[(size_t)rr * ld] = x[rr];
+                        if (ok) dst[LDC ? (size_t)(rr * LDC) : (size_t)rr * ld] = x[rr];
                     }
                 }
                 const float2 vk = vnew[k];               // zero at and left of column j
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     }
 }
 
-template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED>
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC>
 int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
                     float* tau, float2* ph) {
     constexpr int WD = EPL * 32;
@@ -471,7 +475,7 @@ int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int
     size_t tb = (size_t)nts * nts * sizeof(float2);
     if (tb < partb) tb = partb;
     const size_t smem = vec + tb;
-    auto kern = tridiag_symdefer_kernel<EPL, TR, NB, NT, DB, RAGGED>;
+    auto kern = tridiag_symdefer_kernel<EPL, TR, NB, NT, DB, RAGGED, LDC>;
     VK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, NT, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
     VK_LAUNCH_CHECK(h);
@@ -483,12 +487,15 @@ template <int EPL>
 int launch_symdefer_r(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
                       float* tau, float2* ph, int variant) {
     const bool ragged = (r % 32) != 0;
+    const bool full = !ragged && ld == EPL * 32;   // the usual case: r = ld = 256 / 384 / 512
     if (variant == 1) {
-        if (ragged) return launch_symdefer<EPL, 16, 6, 256, false, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
-        return launch_symdefer<EPL, 16, 6, 256, false, false>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+        if (ragged) return launch_symdefer<EPL, 16, 6, 256, false, true, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+        if (full) return launch_symdefer<EPL, 16, 6, 256, false, false, EPL * 32>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+        return launch_symdefer<EPL, 16, 6, 256, false, false, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     }
-    if (ragged) return launch_symdefer<EPL, 8, 8, 512, true, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
-    return launch_symdefer<EPL, 8, 8, 512, true, false>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    if (ragged) return launch_symdefer<EPL, 8, 8, 512, true, true, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    if (full) return launch_symdefer<EPL, 8, 8, 512, true, false, EPL * 32>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+    return launch_symdefer<EPL, 8, 8, 512, true, false, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
 }
 
 }  // namespace
