@@ -13,9 +13,9 @@ for i in range(0, len(a), 4):
     eng.synth_fill(A, B // 4, 4)
     eng.set_option("eig_impl", 2)
     ref = None
-    for impl, var in ((2, 0), (0, 1), (0, 1), (0, 2), (0, 2)):
+    for impl, var in ((0, -1), (0, 0), (0, 32), (0, 64), (0, 96), (0, 128)):
         eng.set_option("tridiag_impl", impl)
-        eng.set_option("tridiag_variant", var)
+        eng.set_option("tridiag_nts", var)
         eng.set_option("stage_timing", 2)
         kw = dict(compressionrank=k) if k > 0 else dict(decorrelation=0.99)
         torch.cuda.synchronize()
@@ -31,4 +31,4 @@ for i in range(0, len(a), 4):
         print(f"B={B} {m}x{n} k={k} tridiag_impl={impl} variant={var}: compress {e0.elapsed_time(e1):.3f} ms, max rel dS vs impl 1 {dev:.2e}", flush=True)
     eng.set_option("stage_timing", 0)
     eng.set_option("tridiag_impl", 0)
-    eng.set_option("tridiag_variant", 0)
+    eng.set_option("tridiag_nts", -1)

@@ -450,6 +450,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->eig_impl = (int)v;
     else if (k == "tridiag_impl")
         h->tridiag_impl = (int)v;
+    else if (k == "tridiag_nts")
+        h->tridiag_nts = (int)v;
     else if (k == "tail_split")
         h->tail_split = (int)v;
     else if (k == "factors_impl")

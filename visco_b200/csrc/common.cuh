@@ -48,6 +48,7 @@ struct vk_context {
     bool in_split = false;
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t tail_ev[2] = {nullptr, nullptr};
+    int tridiag_nts = -1;     // tridiag_sym.cu: largest trailing block that moves to shared memory (-1: whatever fits)
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems

@@ -472,6 +472,10 @@ int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int
     const size_t partb = (size_t)(NT / 32) * WD * sizeof(float2);
     int nts = budget > vec ? (int)sqrt((double)(budget - vec) / sizeof(float2)) : 0;
     if (nts > r) nts = r;
+    // the resident steps only pay for the last few dozen rows (measured at r = 256: 155 rows 1.50, 128: 1.51, 96: 1.47,
+    // 64: 1.46, 32: 1.48, none: 1.52 ms; no difference at r = 512); "tridiag_nts" overrides the cap
+    const int cap = h->tridiag_nts >= 0 ? h->tridiag_nts : 64;
+    if (cap < nts) nts = cap;
     size_t tb = (size_t)nts * nts * sizeof(float2);
     if (tb < partb) tb = partb;
     const size_t smem = vec + tb;
