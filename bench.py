@@ -54,7 +54,7 @@ NCUBES = {"kat7": 4, "meerkat": 1, "small": 4, "small_jacobi": 4}
 OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload runs with (reset afterwards)
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
 # (one CTA per matrix: 112 of 148 SMs at the KAT-7 shape, host polls in between) overlaps the other stages of the next
-HANDLES = {"kat7": 3, "meerkat": 1, "small": 3, "small_jacobi": 3}
+HANDLES = {"kat7": 6, "meerkat": 1, "small": 6, "small_jacobi": 6}   # upper bound: never more than the rank's share of the host cores
 E2E_THREADS = int(os.environ.get("VISCO_E2E_THREADS", "0"))   # 0: six, or as many as the rank's share of the host cores allows
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
 
@@ -338,7 +338,9 @@ def run_workload(eng, Engine, torch, dist, dev, world, rank, name, steps, warmup
             dist.barrier()
         torch.cuda.synchronize()
 
-    nh = int(os.environ.get("VISCO_BENCH_HANDLES", HANDLES[name]))
+    # concurrent handles (one host thread + stream each), measured on the KAT-7 cube: 1: 2.40, 2: 1.80, 3: 1.40, 4: 1.32,
+    # 6: 1.26 ms per cube - the kernels that leave SMs idle for one cube (112 matrices on 148 SMs) are filled by the others
+    nh = int(os.environ.get("VISCO_BENCH_HANDLES", 0)) or max(1, min(HANDLES[name], len(os.sched_getaffinity(0)) // max(1, world)))
     engines = [eng] + [Engine(eng.device) for _ in range(nh - 1)]
     for e_ in engines:
         for k_, v_ in OPTIONS.get(name, {}).items():
