@@ -72,7 +72,21 @@ int vk_sync(vk_handle h);
  *          rank is <= 30 - pays on high-SNR data where most matrices qualify),
  *          "illcond_thr" (default 0.005: a matrix whose smallest retained singular value is below that * sigma_1 cannot be
  *          resolved through the float32 Gram matrix and is done again by one-sided Jacobi on the matrix itself; 0 = never),
- *          "ql_maxit" (QL iterations per eigenvalue before the pass is handed to the Jacobi solver, default 60). */
+ *          "ql_maxit" (QL iterations per eigenvalue before the pass is handed to the Jacobi solver, default 60),
+ *          "eigvec_impl" (full spectrum with eig_impl 0/2: 0 = bisection + twisted factorisation + Newton-Schulz + tcgen05
+ *          GEMMs, 1 = implicit QL with recorded rotations),
+ *          "tridiag_impl" (0 = lower triangle with deferred updates for 128 < min(m,n) <= 512 and the warp-level kernel for
+ *          <= 64, 1 = round 1's undeferred full-storage kernels, 2 = full storage with deferred updates),
+ *          "tridiag_variant" (launch shape of the lower-triangle kernel: 0 = two matrices per SM when the batch exceeds the
+ *          SM count or three or more host threads are inside vk_compress_batched on this device, else one; 1 / 2 force
+ *          one / two), "tridiag_nts" (rows of the trailing block that finish in shared memory, default 64),
+ *          "tail_split" (0 = the remainder of a batch that is not a whole number of waves runs as its own sub-batch on a
+ *          second stream, 1 = off),
+ *          "small_impl" (one-sided Jacobi on the matrix itself: 0 = for min(m,n) <= 32 when it fits one CTA, 1 = for every
+ *          shape that fits (min(m,n) <= 64: BASELINE configs[3] as named), 2 = never),
+ *          "factors_impl" (small ranks, wide matrices: 0 = one fused cluster kernel, 1 = the separate kernels),
+ *          "recon_tc_impl" (8 < k <= 32: 0 = persistent tcgen05 kernel with bulk tensor stores, 1 = the older kernels).
+ *          Every choice of these leaves the results within the tolerances of DESIGN.md section 2. */
 int vk_set_option(vk_handle h, const char* key, double value);
 /* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own
  * workspace when ws == NULL). */
