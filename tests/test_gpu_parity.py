@@ -571,3 +571,27 @@ def test_stage_and_kernel_timers_of_the_c_abi(eng, torch):
         assert eig["ql"] > 0 and eig["reflectors"] > 0 and eig["rotations"] > 0   # energy rule: the full QL route
     finally:
         eng.set_option("stage_timing", 0)
+
+
+@pytest.mark.parametrize("scale", [1e25, 3e-26])
+@pytest.mark.parametrize("shape,kw", [((256, 512), dict(compressionrank=6)), ((96, 300), dict(decorrelation=0.97)),
+                                       ((200, 16), dict(compressionrank=4))])
+def test_inputs_whose_squares_leave_the_float32_range(eng, torch, scale, shape, kw):
+    """|a| ~ 1e25 overflows, |a| ~ 1e-26 vanishes in a float32 Gram product (LAPACK's cgesdd scales its input). Such matrices
+    are detected by their trace and done again without a Gram product, on data scaled by a power of two; a genuinely
+    non-finite input is still an error."""
+    rng = np.random.default_rng(5)
+    m, n = shape
+    B = 3
+    a = (rng.standard_normal((B, m, n)) + 1j * rng.standard_normal((B, m, n))).astype(np.complex64)
+    a[:, : m // 4] *= 6.0                                        # some structure in the spectrum
+    a[1] *= np.float32(scale)                                    # one matrix of the batch is out of range, its neighbours are not
+    U, S, Vt, ranks, stats = (x.cpu().numpy() for x in eng.compress(torch.from_numpy(a).cuda(), **kw))
+    for b in range(B):
+        k = int(ranks[b])
+        assert np.isfinite(S[b, :k]).all() and S[b, 0] > 0
+        parity.check_factors(a[b], U[b, :, :k], S[b, :k], Vt[b, :k], k, label=f"scaled {scale} {shape} b={b}", **kw)
+    bad = a.copy()
+    bad[2, 1, 1] = np.nan
+    with pytest.raises(ValueError):
+        eng.compress(torch.from_numpy(bad).cuda(), **kw)

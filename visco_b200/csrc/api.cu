@@ -158,7 +158,8 @@ struct StageTimer {
     }
 };
 
-int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale, int32_t* nonfinite) {
+int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale, int32_t* nonfinite,
+               int32_t* bad = nullptr, int32_t* nbad = nullptr) {
     const int r = m < n ? m : n;
     const int side = m <= n ? 0 : 1;
     int rc;
@@ -172,7 +173,7 @@ int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, f
     } else {
         if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;
     }
-    return vk_launch_gram_normalise(h, W, B, r, gscale, nonfinite);
+    return vk_launch_gram_normalise(h, W, B, r, gscale, nonfinite, bad, nbad);
 }
 
 int compress_chunk(vk_context* h, const float2* A, int B, int m, int n, int fixed_rank, double decorrelation, int kmax,
@@ -273,16 +274,24 @@ int redo_ill_conditioned(vk_context* h, const float2* A, int B, int m, int n, in
     if ((rc = ensure(h, &h->ws2, &h->ws2_bytes, fbytes))) return rc;
     int32_t* flags = static_cast<int32_t*>(h->ws2);
     int32_t* count = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(h->ws2) + align_up((size_t)B * 4));
-    if ((rc = vk_launch_flag_illcond(h, S, ranks, B, kmax, h->illcond_thr, flags, count))) return rc;
-    VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 3, count, 4, cudaMemcpyDeviceToHost, h->stream));
+    h->h_poll[3] = 0;
+    if (h->illcond_thr > 0.f) {
+        if ((rc = vk_launch_flag_illcond(h, S, ranks, B, kmax, h->illcond_thr, flags, count))) return rc;
+        VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 3, count, 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    // ... plus the matrices whose Gram trace left the float32-safe range (h->bad, set by the normalisation kernel)
+    h->h_poll[4] = 0;
+    if (h->bad) VK_CUDA(h, cudaMemcpyAsync(h->h_poll + 4, h->bad + B, 4, cudaMemcpyDeviceToHost, h->stream));
     VK_CUDA(h, cudaStreamSynchronize(h->stream));
-    const int nflag = h->h_poll[3];
-    if (nflag <= 0) return VK_OK;
-    std::vector<int32_t> hf((size_t)B);
-    VK_CUDA(h, cudaMemcpy(hf.data(), flags, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    const int nflag = h->h_poll[3], nbad = h->h_poll[4];
+    if (nflag <= 0 && nbad <= 0) return VK_OK;
+    std::vector<int32_t> hf((size_t)B, 0), hb((size_t)B, 0);
+    if (nflag > 0) VK_CUDA(h, cudaMemcpy(hf.data(), flags, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (nbad > 0) VK_CUDA(h, cudaMemcpy(hb.data(), h->bad, (size_t)B * 4, cudaMemcpyDeviceToHost));
     std::vector<int> idx;
     for (int b = 0; b < B; ++b)
-        if (hf[b]) idx.push_back(b);
+        if (hf[b] || hb[b]) idx.push_back(b);
+    if (idx.empty()) return VK_OK;
     const size_t bA = (size_t)m * n * 8, bU = (size_t)m * kmax * 8, bS = (size_t)kmax * 4, bV = (size_t)kmax * n * 8;
     const size_t per = align_up(bA) + align_up(bU) + align_up(bS) + align_up(bV) + 512 +
                        ws_layout(h, 1, m, n, kmax, 1, false, true).total;
@@ -378,6 +387,7 @@ int vk_destroy(vk_handle h) {
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     if (h->ws2) cudaFree(h->ws2);
+    if (h->bad) cudaFree(h->bad);
     if (h->h_poll) cudaFreeHost(h->h_poll);
     if (h->d_scratch) cudaFree(h->d_scratch);
     for (auto& e : h->ev)
@@ -525,6 +535,14 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
     float2* Up = static_cast<float2*>(U);
     float2* Vp = static_cast<float2*>(Vt);
     const bool gram_path = !small_path(h, m, n);
+    if (gram_path) {
+        // per-matrix flags of Gram traces outside the float32-safe range (input beyond ~1e19 or below ~1e-19): those
+        // matrices are done again without a Gram product after the main loop
+        void* pb = h->bad;
+        if ((rc = ensure(h, &pb, &h->bad_bytes, ((size_t)B + 1) * 4))) return rc;
+        h->bad = static_cast<int32_t*>(pb);
+        VK_CUDA(h, cudaMemsetAsync(h->bad, 0, ((size_t)B + 1) * 4, h->stream));
+    }
     for (int g0 = 0; g0 < B; g0 += gchunk) {
         const int ng = (B - g0) < gchunk ? (B - g0) : gchunk;
         if (gram_path) {
@@ -534,7 +552,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
             StageTimer tg(h);
             tg.mark(0);
             rc = gram_stage(h, Ap + (size_t)g0 * m * n, ng, m, n, reinterpret_cast<float2*>(wsp + L.W),
-                            reinterpret_cast<float*>(wsp + L.gscale), nonfinite);
+                            reinterpret_cast<float*>(wsp + L.gscale), nonfinite, h->bad + g0, h->bad + B);
             if (rc) return rc;
             tg.mark(1);
             tg.collect(0, 0, 1);
@@ -548,7 +566,7 @@ int vk_compress_batched(vk_handle h, const void* A, int B, int m, int n, int fix
             if (rc) return rc;
         }
     }
-    if (gram_path && h->illcond_thr > 0.f) {
+    if (gram_path) {
         rc = redo_ill_conditioned(h, Ap, B, m, n, fixed_rank, decorrelation, kmax, Up, S, Vp, ranks, stats);
         if (rc) return rc;
     }

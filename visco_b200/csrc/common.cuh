@@ -49,6 +49,8 @@ struct vk_context {
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t tail_ev[2] = {nullptr, nullptr};
     int tridiag_nts = -1;     // tridiag_sym.cu: largest trailing block that moves to shared memory (-1: whatever fits)
+    int32_t* bad = nullptr;   // per-matrix flags of the current vk_compress_batched call: Gram trace outside the safe range
+    size_t bad_bytes = 0;     // (grow-only; bad[B] is the count)
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels
     int recon_generic = 0;   // 1 = always use the generic GEMM reconstruction kernel (debug / comparison)
     int small_reg = 1;       // 1 = register-resident recursive tournament for power-of-two small problems
@@ -150,7 +152,9 @@ int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float
 bool vk_gram_tc_supported(int m, int n, int side);
 
 // scale[b] = r / trace(W[b]) applied in place; gscale_dev[b] = trace/r ; nonfinite_dev[0] |= 1 when trace is NaN/Inf
-int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev);
+// bad_dev / nbad_dev (optional): per-matrix flag and count of traces outside the float32-safe range (see stages.cu)
+int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev,
+                             int32_t* bad_dev = nullptr, int32_t* nbad_dev = nullptr);
 
 // small path: build [B][r][ld] vectors (rows of A, or columns when m > n) followed by an r x r identity
 int vk_launch_pack_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, int ld, float* gscale_dev,

@@ -50,8 +50,13 @@ struct GramOp1 {  // W[i][j] = sum_t A[t][i] * conj(A[t][j])          (r = n)
 };
 
 // scale W[b] so that trace == r; gscale[b] = trace / r. One CTA per matrix.
+// A trace that is not finite, or outside [1e-30, 1e30] * r, means the squares of the input left the float32 range (|a| beyond
+// ~1e19 or below ~1e-19; LAPACK scales such input): the matrix is replaced by the identity so that the stages behind stay
+// harmless, bad[b] is set, and the driver does it again without a Gram product (api.cu). NaN / Inf input ends up there
+// too and is reported by that path.
 __global__ void __launch_bounds__(1024) gram_normalise_kernel(float2* __restrict__ W, int r, float* __restrict__ gscale,
-                                                             int32_t* __restrict__ nonfinite) {
+                                                             int32_t* __restrict__ nonfinite, int32_t* __restrict__ bad,
+                                                             int32_t* __restrict__ nbad) {
     __shared__ float part[32];
     __shared__ float sc;
     const int b = blockIdx.x;
@@ -65,17 +70,30 @@ __global__ void __launch_bounds__(1024) gram_normalise_kernel(float2* __restrict
         float tr = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tr += part[w];
         float g = tr / (float)r;
-        if (!isfinite(g)) {
-            atomicOr(nonfinite, 1);
+        bool isbad = false;
+        // (a trace of exactly zero is either a zero matrix or input whose squares vanished: the second pass tells)
+        if (!isfinite(g) || fabsf(g) < 1e-30f || fabsf(g) > 1e30f) {
+            if (bad) {
+                isbad = true;
+                bad[b] = 1;
+                atomicAdd(nbad, 1);
+            } else if (!isfinite(g)) {
+                atomicOr(nonfinite, 1);
+            }
             g = 1.f;
         }
         if (!(g > 0.f)) g = 1.f;  // all-zero matrix: leave it alone
         gscale[b] = g;
-        sc = 1.f / g;
+        sc = isbad ? -1.f : 1.f / g;
     }
     __syncthreads();
     const float f = sc;
     const size_t tot = (size_t)r * r;
+    if (f < 0.f) {   // out-of-range matrix: identity
+        for (size_t e = threadIdx.x; e < tot; e += blockDim.x)
+            Wb[e] = make_float2((e / r == e % r) ? 1.f : 0.f, 0.f);
+        return;
+    }
     if ((tot & 1) == 0) {  // two complex numbers per access (the matrix base is 16-byte aligned when r*r is even)
         float4* W4 = reinterpret_cast<float4*>(Wb);
         const size_t n4 = tot >> 1;
@@ -105,24 +123,45 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restric
     const float2* Ab = A + (size_t)b * m * n;
     const int r = m <= n ? m : n;
     const int L = m <= n ? n : m;
+    // largest magnitude first: the squares are summed on data scaled by a power of two into [1, 2) at the top, so inputs
+    // of any float32 magnitude neither overflow nor vanish here (LAPACK's cgesdd scales the same way)
+    __shared__ int s_exp;
+    float amax = 0.f;
+    for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
+        const float2 v = Ab[e];
+        amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
+        if (!isfinite(v.x) || !isfinite(v.y)) amax = __int_as_float(0x7f800000);
+    }
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, part[w]);
+        int ex = 0;
+        if (!isfinite(mx)) atomicOr(nonfinite, 1);
+        else if (mx > 0.f) ex = ilogbf(mx);
+        s_exp = ex;
+    }
+    __syncthreads();
+    const int ex = s_exp;
     float s = 0.f;
     for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
         const float2 v = Ab[e];
-        s = fmaf(v.x, v.x, fmaf(v.y, v.y, s));
+        const float x = scalbnf(v.x, -ex), y = scalbnf(v.y, -ex);
+        s = fmaf(x, x, fmaf(y, y, s));
     }
     s = warp_sum(s);
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
         float tot = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
         float g = sqrtf(tot / (float)r);
-        if (!isfinite(g)) {
-            atomicOr(nonfinite, 1);
-            g = 1.f;
-        }
+        if (!isfinite(g)) g = 1.f;
         if (!(g > 0.f)) g = 1.f;
-        gscale[b] = g;
+        gscale[b] = scalbnf(g, ex);
         sc = 1.f / g;
     }
     __syncthreads();
@@ -132,8 +171,8 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restric
         for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
             const int i = e / n, x = e - i * n;
             float2 v = Ab[e];
-            v.x *= f;
-            v.y *= f;
+            v.x = scalbnf(v.x, -ex) * f;
+            v.y = scalbnf(v.y, -ex) * f;
             Wb[(size_t)i * ld + x] = v;
         }
     } else {
@@ -141,8 +180,8 @@ __global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restric
         for (int e = threadIdx.x; e < m * n; e += blockDim.x) {
             const int t = e / n, j = e - t * n;
             float2 v = Ab[e];
-            v.x *= f;
-            v.y *= f;
+            v.x = scalbnf(v.x, -ex) * f;
+            v.y = scalbnf(v.y, -ex) * f;
             Wb[(size_t)j * ld + t] = v;
         }
     }
@@ -887,8 +926,9 @@ int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int
     return cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
 }
 
-int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev) {
-    gram_normalise_kernel<<<B, r >= 128 ? 1024 : 256, 0, h->stream>>>(W, r, gscale_dev, nonfinite_dev);
+int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev,
+                             int32_t* bad_dev, int32_t* nbad_dev) {
+    gram_normalise_kernel<<<B, r >= 128 ? 1024 : 256, 0, h->stream>>>(W, r, gscale_dev, nonfinite_dev, bad_dev, nbad_dev);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
