@@ -1670,26 +1670,56 @@ __global__ void __launch_bounds__(EV_THREADS) twisted_full_kernel(int r, const f
         dp[0] = p;
         float best = fabsf(q);  // gamma_0 = dm[0]
         int kt = 0;
-        for (int i = 1; i < r; ++i) {
-            const float ei = e[i - 1];
-            p = d[i] - lam - ei * ei / p;
-            if (fabsf(p) < pivmin) p = -pivmin;
-            dp[(size_t)i * r] = p;
-            const float gam = fabsf(p + dm[(size_t)i * r] - (d[i] - lam));
-            if (gam < best) best = gam, kt = i;
+        // (the pivots written above come back from L2: they are fetched eight steps ahead of the recurrences that use them -
+        // fetched inside the dependent loops the kernel ran at 12 % issue utilisation, latency bound)
+        constexpr int PF = 8;
+        for (int i0 = 1; i0 < r; i0 += PF) {
+            float dmv[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) dmv[u] = (i0 + u < r) ? dm[(size_t)(i0 + u) * r] : 0.f;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int i = i0 + u;
+                if (i < r) {
+                    const float ei = e[i - 1];
+                    p = d[i] - lam - ei * ei / p;
+                    if (fabsf(p) < pivmin) p = -pivmin;
+                    dp[(size_t)i * r] = p;
+                    const float gam = fabsf(p + dmv[u] - (d[i] - lam));
+                    if (gam < best) best = gam, kt = i;
+                }
+            }
         }
         // z[kt] = 1; upward with the forward pivots, downward with the backward ones (z overwrites dp)
         float nrm = 1.f, zi = 1.f;
-        for (int i = kt - 1; i >= 0; --i) {
-            zi = -(e[i] / dp[(size_t)i * r]) * zi;
-            dp[(size_t)i * r] = zi;
-            nrm = fmaf(zi, zi, nrm);
+        for (int i0 = kt - 1; i0 >= 0; i0 -= PF) {
+            float dpv[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) dpv[u] = (i0 - u >= 0) ? dp[(size_t)(i0 - u) * r] : 1.f;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int i = i0 - u;
+                if (i >= 0) {
+                    zi = -(e[i] / dpv[u]) * zi;
+                    dp[(size_t)i * r] = zi;
+                    nrm = fmaf(zi, zi, nrm);
+                }
+            }
         }
         zi = 1.f;
-        for (int i = kt + 1; i < r; ++i) {
-            zi = -(e[i - 1] / dm[(size_t)i * r]) * zi;
-            dp[(size_t)i * r] = zi;
-            nrm = fmaf(zi, zi, nrm);
+        for (int i0 = kt + 1; i0 < r; i0 += PF) {
+            float dmv[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) dmv[u] = (i0 + u < r) ? dm[(size_t)(i0 + u) * r] : 1.f;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int i = i0 + u;
+                if (i < r) {
+                    zi = -(e[i - 1] / dmv[u]) * zi;
+                    dp[(size_t)i * r] = zi;
+                    nrm = fmaf(zi, zi, nrm);
+                }
+            }
         }
         dp[(size_t)kt * r] = 1.f;
         sc = rsqrtf(nrm);
