@@ -1616,9 +1616,26 @@ __global__ void __launch_bounds__(EV_THREADS) bisect_full_kernel(int r, const fl
     const float scale = fmaxf(fabsf(lo), fabsf(hi));
     const float pivmin = fmaxf(1e-30f, 1e-14f * scale * scale);
     const int t = blockIdx.x * EV_THREADS + tid;  // t-th largest eigenvalue
+    float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+    // first level shared by the block: Sturm counts at EV_THREADS equispaced points, one per thread; every thread then starts
+    // from the grid cell that holds its eigenvalue (saves log2(EV_THREADS) of its own bisection steps)
+    __shared__ int s_cnt[EV_THREADS + 1];
+    const float g0 = a, gh = (c - a) * (1.f / EV_THREADS);
+    s_cnt[tid + 1] = tid + 1 < EV_THREADS ? sturm_count(d, e2, r, g0 + gh * (float)(tid + 1), pivmin) : r;
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
     if (t >= r) return;
     const int idx = r - 1 - t;
-    float a = lo - 1e-6f * scale - 1e-30f, c = hi + 1e-6f * scale + 1e-30f;
+    {
+        int q0 = 0, q1 = EV_THREADS;          // invariant: s_cnt[q0] <= idx < s_cnt[q1]
+        while (q1 - q0 > 1) {
+            const int qm = (q0 + q1) >> 1;
+            if (s_cnt[qm] > idx) q1 = qm;
+            else q0 = qm;
+        }
+        if (q1 < EV_THREADS) c = g0 + gh * (float)q1;
+        if (q0 > 0) a = g0 + gh * (float)q0;
+    }
     for (int it = 0; it < 48; ++it) {
         const float mid = 0.5f * (a + c);
         if (!(mid > a && mid < c)) break;
