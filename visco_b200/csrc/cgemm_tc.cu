@@ -91,7 +91,8 @@ struct GemmArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapD, const GemmArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
@@ -271,32 +272,43 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
 
-        // ---- epilogue: this thread holds row (m0 + quad*32 + lane), complex columns n0c + chalf*64 .. +63 ----
+        // ---- epilogue: this thread holds row (m0 + quad*32 + lane), complex columns n0c + chalf*64 .. +63 = 512 bytes. Stored
+        // straight from the registers every warp instruction touches 32 rows with 16 bytes each (half sectors); instead the
+        // warp stages its 32 x 64 block in the (now idle) operand stages - four TMA boxes of 32 rows x 128 bytes,
+        // SWIZZLE_128B: a lane writes its own row, the 16-byte chunk index XOR-ed with the row keeps the stores conflict
+        // free - and one lane hands them to the TMA unit, which also clips at the ragged ends of M and N ----
         const int gi = m0 + quad * 32 + lane;
-        if (gi < g.Mtot) {
-            const bool valid_row = gi < Mvalid;
-            float2* drow = g.D + ((size_t)b * g.Mtot + gi) * g.Ntot;
-            float nsum = 0.f;
-            float rs = 1.f, rsi = 1.f;
-            if (MODE == MODE_PLAIN && g.rowscale) {
-                rs = g.rowscale[(size_t)b * g.Mtot + gi];
-                rsi = -rs;
-            }
+        const bool valid_row = gi < Mvalid;
+        float nsum = 0.f;
+        float rs = 1.f, rsi = 1.f;
+        if (MODE == MODE_PLAIN && g.rowscale && gi < g.Mtot) {
+            rs = g.rowscale[(size_t)b * g.Mtot + gi];
+            rsi = -rs;
+        }
+        const uint32_t stg = sbase + (uint32_t)(warp - 4) * 16384u + (uint32_t)lane * 128u;
 #pragma unroll
-            for (int j = 0; j < 64; j += 2) {
-                const int v = n0c + chalf * 64 + j;
-                float4 o = valid_row ? make_float4(acc[2 * j], acc[2 * j + 1], acc[2 * j + 2], acc[2 * j + 3])
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MODE == MODE_PLAIN) o = make_float4(rs * o.x, rsi * o.y, rs * o.z, rsi * o.w);
-                if (v + 1 < g.Ntot) {
-                    *reinterpret_cast<float4*>(drow + v) = o;
-                    nsum += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-                } else if (v < g.Ntot) {
-                    drow[v] = make_float2(o.x, o.y);
-                    nsum += o.x * o.x + o.y * o.y;
-                }
+        for (int j = 0; j < 64; j += 2) {
+            const int v = n0c + chalf * 64 + j;
+            float4 o = valid_row ? make_float4(acc[2 * j], acc[2 * j + 1], acc[2 * j + 2], acc[2 * j + 3])
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == MODE_PLAIN) o = make_float4(rs * o.x, rsi * o.y, rs * o.z, rsi * o.w);
+            if (MODE == MODE_FORMV) {
+                if (v + 1 < g.Ntot) nsum += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+                else if (v < g.Ntot) nsum += o.x * o.x + o.y * o.y;
             }
-            if (MODE == MODE_FORMV && valid_row) atomicAdd(&g.norm2[(size_t)b * g.kmax + gi], nsum);
+            const int box = j >> 4, cc = (j & 15) >> 1;      // 16 complex columns per box, two per 16-byte chunk
+            sts128(stg + (uint32_t)box * 4096u + (uint32_t)((cc ^ (lane & 7)) << 4), o);
+        }
+        if (MODE == MODE_FORMV && valid_row && gi < g.Mtot) atomicAdd(&g.norm2[(size_t)b * g.kmax + gi], nsum);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t wbase = sbase + (uint32_t)(warp - 4) * 16384u;
+            const int c0 = 2 * (n0c + chalf * 64), c1 = m0 + quad * 32;
+#pragma unroll
+            for (int box = 0; box < 4; ++box) tma_store_3d(&mapD, wbase + box * 4096u, c0 + box * 32, c1, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the bulk reads
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -319,6 +331,19 @@ int make_map_a(vk_context* h, CUtensorMap* map, const float2* P, int rows, int k
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (A operand) failed: " + std::to_string((int)r));
+    return VK_OK;
+}
+// output D[b][rows][nc] complex: real view dims (2*nc, rows, B); boxes of 32 rows x 128 bytes
+int make_map_d(vk_context* h, CUtensorMap* map, float2* D, int rows, int nc, int nb) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * nc, (cuuint64_t)rows, (cuuint64_t)nb};
+    const cuuint64_t strides[2] = {(cuuint64_t)nc * 8, (cuuint64_t)rows * nc * 8};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, D, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vk_fail(h, VK_ECUDA, "tensor map (output) failed: " + std::to_string((int)r));
     return VK_OK;
 }
 // B operand: Q[b][krows][nc] complex, N contiguous: view (32 floats, krows, 2*nc/32 groups, B); box {32, KB_C, 8, 1}
@@ -350,10 +375,11 @@ int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const in
     const int maxB = 16384;
     for (int b0 = 0; b0 < B; b0 += maxB) {
         const int nb = (B - b0) < maxB ? (B - b0) : maxB;
-        CUtensorMap ma, mb;
+        CUtensorMap ma, mb, md;
         int rc;
         if ((rc = make_map_a(h, &ma, X + (size_t)b0 * kmax * m, kmax, m, nb))) return rc;
         if ((rc = make_map_b(h, &mb, A + (size_t)b0 * m * n, m, n, nb))) return rc;
+        if ((rc = make_map_d(h, &md, Vt + (size_t)b0 * kmax * n, kmax, n, nb))) return rc;
         GemmArgs g;
         g.D = Vt + (size_t)b0 * kmax * n;
         g.ranks = ranks + b0;
@@ -366,7 +392,7 @@ int vk_launch_formv_tc(vk_context* h, const float2* X, const float2* A, const in
         g.kmax = kmax;
         g.tiles_m = (kmax + TILE_M - 1) / TILE_M;
         g.tiles_n = (n + TILE_NC - 1) / TILE_NC;
-        cgemm_tc_kernel<MODE_FORMV><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        cgemm_tc_kernel<MODE_FORMV><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, md, g);
         VK_LAUNCH_CHECK(h);
     }
     return VK_OK;
@@ -382,10 +408,11 @@ int vk_launch_cgemm_tc_plain(vk_context* h, const float2* P, const float2* Q, fl
     const int maxB = 16384;
     for (int b0 = 0; b0 < B; b0 += maxB) {
         const int nb = (B - b0) < maxB ? (B - b0) : maxB;
-        CUtensorMap ma, mb;
+        CUtensorMap ma, mb, md;
         int rc;
         if ((rc = make_map_a(h, &ma, P + (size_t)b0 * M * K, M, K, nb))) return rc;
         if ((rc = make_map_b(h, &mb, Q + (size_t)b0 * K * N, K, N, nb))) return rc;
+        if ((rc = make_map_d(h, &md, D + (size_t)b0 * M * N, M, N, nb))) return rc;
         GemmArgs g;
         g.D = D + (size_t)b0 * M * N;
         g.ranks = nullptr;
@@ -398,7 +425,7 @@ int vk_launch_cgemm_tc_plain(vk_context* h, const float2* P, const float2* Q, fl
         g.kmax = K;
         g.tiles_m = (M + TILE_M - 1) / TILE_M;
         g.tiles_n = (N + TILE_NC - 1) / TILE_NC;
-        cgemm_tc_kernel<MODE_PLAIN><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        cgemm_tc_kernel<MODE_PLAIN><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, md, g);
         VK_LAUNCH_CHECK(h);
     }
     return VK_OK;
@@ -411,10 +438,11 @@ int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const flo
     const int maxB = 16384;
     for (int b0 = 0; b0 < B; b0 += maxB) {
         const int nb = (B - b0) < maxB ? (B - b0) : maxB;
-        CUtensorMap ma, mb;
+        CUtensorMap ma, mb, md;
         int rc;
         if ((rc = make_map_a(h, &ma, U + (size_t)b0 * m * kmax, m, kmax, nb))) return rc;
         if ((rc = make_map_b(h, &mb, Vt + (size_t)b0 * kmax * n, kmax, n, nb))) return rc;
+        if ((rc = make_map_d(h, &md, out + (size_t)b0 * m * n, m, n, nb))) return rc;
         GemmArgs g;
         g.D = out + (size_t)b0 * m * n;
         g.ranks = ranks ? ranks + b0 : nullptr;
@@ -427,7 +455,7 @@ int vk_launch_recon_tc(vk_context* h, const float2* U, const float* S, const flo
         g.kmax = kmax;
         g.tiles_m = (m + TILE_M - 1) / TILE_M;
         g.tiles_n = (n + TILE_NC - 1) / TILE_NC;
-        cgemm_tc_kernel<MODE_RECON><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, g);
+        cgemm_tc_kernel<MODE_RECON><<<(unsigned)((long long)nb * g.tiles_m * g.tiles_n), NUM_THREADS, SMEM_BYTES, h->stream>>>(ma, mb, md, g);
         VK_LAUNCH_CHECK(h);
     }
     return VK_OK;

@@ -58,13 +58,6 @@ struct TileRef {
     int b, m0, n0c, t;
 };
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-
 // Drain one finished tile: TMEM -> registers (one accumulator row per thread) -> complex values -> the warp's own 8 KiB
 // staging block in shared memory (two TMA boxes of 32 rows x 128 bytes, SWIZZLE_128B: a lane writes its own row, the
 // 16-byte chunk index XOR-ed with the row keeps the 128-bit stores conflict free) -> HBM by two bulk tensor stores that one

@@ -44,6 +44,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// bulk tensor store of one box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // K-major SWIZZLE_128B operand: rows of 128 bytes, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t saddr) {
     uint64_t d = 0;
