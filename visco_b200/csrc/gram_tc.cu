@@ -71,8 +71,8 @@ __device__ __forceinline__ void drain_chunk(int c, uint32_t bar_accf, uint32_t b
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W, int m, int n2, int tiles_per_mat,
-               int T) {
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap mapW, int tma_store,
+               float2* __restrict__ W, int m, int n2, int tiles_per_mat, int T) {
     extern __shared__ unsigned char smem_raw[];
     // swizzled operands need 1024-byte alignment
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -216,11 +216,34 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
         const int i_loc = quad * 32 + lane;   // row of the tile = TMEM lane
         const int gi = I * TILE + i_loc;
         float2* Wb = W + (size_t)b * m * m;
-        if (gi < m) {
+        if (tma_store) {
+            // the tile itself: staged per warp in the (now idle) operand stages - four boxes of 32 rows x 128 bytes,
+            // SWIZZLE_128B - and stored by the TMA unit, clipped at the ragged edge of m (from the registers a warp
+            // instruction touched 32 rows with 8 bytes each)
+            const uint32_t stg = sbase + (uint32_t)(warp - 4) * 16384u + (uint32_t)lane * 128u;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int gt = J * TILE + chalf * 64 + j;
-                if (gt < m) Wb[(size_t)gi * m + gt] = make_float2(acc_re[j], acc_im[j]);
+            for (int j = 0; j < 64; j += 2) {
+                const int box = j >> 4, cc = (j & 15) >> 1;
+                sts128(stg + (uint32_t)box * 4096u + (uint32_t)((cc ^ (lane & 7)) << 4),
+                       make_float4(acc_re[j], acc_im[j], acc_re[j + 1], acc_im[j + 1]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t wbase = sbase + (uint32_t)(warp - 4) * 16384u;
+                const int c0 = 2 * (J * TILE + chalf * 64), c1 = I * TILE + quad * 32;
+#pragma unroll
+                for (int box = 0; box < 4; ++box) tma_store_3d(&mapW, wbase + box * 4096u, c0 + box * 32, c1, b);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (gi < m) {
+            if (!tma_store) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int gt = J * TILE + chalf * 64 + j;
+                    if (gt < m) Wb[(size_t)gi * m + gt] = make_float2(acc_re[j], acc_im[j]);
+                }
             }
             if (I != J) {
                 // mirrored tile: W[t][i] = conj(W[i][t]); lanes run along i -> coalesced
@@ -231,6 +254,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, float2* __restrict__ W,
                 }
             }
         }
+        if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem outlives the reads
     }
     __syncthreads();
     if (warp == 2) {
@@ -267,8 +291,21 @@ int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS)
             return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        // output as a 3-D tensor (2m floats, m rows, nb matrices) for the bulk stores of the epilogue (needs 16-byte rows)
+        CUtensorMap mapW = tmap;
+        const int tma_store = (m % 2 == 0) && (reinterpret_cast<uintptr_t>(W) % 16 == 0);
+        if (tma_store) {
+            const cuuint64_t wd[3] = {(cuuint64_t)2 * m, (cuuint64_t)m, (cuuint64_t)nb};
+            const cuuint64_t ws[2] = {(cuuint64_t)m * 8, (cuuint64_t)m * m * 8};
+            const cuuint32_t wb[3] = {32, 32, 1};
+            const CUresult rw = encode(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, W + (size_t)b0 * m * m, wd, ws, wb, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rw != CUDA_SUCCESS)
+                return vk_fail(h, VK_ECUDA, "cuTensorMapEncodeTiled (Gram output) failed with code " + std::to_string((int)rw));
+        }
         gram_tc_kernel<<<(unsigned)(nb * tiles), NUM_THREADS, SMEM_BYTES, h->stream>>>(
-            tmap, W + (size_t)b0 * m * m, m, 2 * n, tiles, T);
+            tmap, mapW, tma_store, W + (size_t)b0 * m * m, m, 2 * n, tiles, T);
         VK_LAUNCH_CHECK(h);
     }
     return VK_OK;
