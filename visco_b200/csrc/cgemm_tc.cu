@@ -28,29 +28,26 @@ using namespace tc;
 
 constexpr int TILE_M = 128;
 constexpr int TILE_NC = 128;              // complex output columns per tile = 256 floats = MMA N
-// K-blocks of 8 complex contraction elements, TWO rings: TMA fills a ring of eight raw slots (16 KiB each), the converter
-// warps split a raw slot into one of two converted slots (48 KiB each) that the tensor core reads. A single ring of stages
-// that go load -> convert -> MMA in place covers only (stages - 1) K-blocks of load latency: with two 112 KiB stages the
-// tensor pipe was 38 % busy, with four 56 KiB stages 46 %. Now seven loads are in flight behind the block being converted
-// and conversion overlaps the MMAs of the block before (10.3 -> 10.0 ms per 296 reconstructions at k = 416). What bounds
-// the kernel from here on is SHARED-MEMORY BANDWIDTH: per K-block TMA writes 16 KiB, the converters read 16 and write
-// 48 KiB, and the six MMAs read 6 x (4 + 8) KiB of operands - 152 KiB = 1190 cycles at 128 B/clk against 786 cycles of MMA
-// time; switching loads, conversions, MMAs or stores off one by one shortened the run additively (each one's share of that
-// traffic), and neither per-warp barrier arrivals nor two converter groups alternating K-blocks changed it. The A operand
-// rows are 16 floats = 64 bytes: SWIZZLE_64B.
+// K-blocks of 8 complex contraction elements in a FOUR-stage ring: with blocks of 16 only two 112 KiB stages fit, and a
+// stage then goes TMA (1.5-2 us from L2 / HBM) -> conversion -> MMA strictly in turn - the tensor pipe was 38 % busy
+// (profiles/r02_ncu_full_c3_gram_cgemm.txt); half-size blocks keep three loads in flight behind the one being multiplied
+// (46 %). What bounds the kernel from here on is SHARED-MEMORY BANDWIDTH: per K-block TMA writes 16 KiB, the converters
+// read 16 and write 48 KiB, and the six MMAs read 6 x (4 + 8) KiB of operands - 152 KiB = 1190 cycles at 128 B/clk against
+// 786 cycles of MMA time; switching loads, conversions, MMAs or stores off one by one shortened a run additively (each
+// one's share of that traffic). Measured and dropped on top of this: a ring of eight raw slots feeding two converted slots
+// (10.0 vs 10.3 ms on 296 equal-rank reconstructions, but 40.5 vs 37.2-38.3 ms on the MeerKAT shard's ragged ranks), one
+// barrier arrival per warp instead of per thread (no change), two converter groups alternating K-blocks (10.7 ms), TMA
+// multicast of the A tile inside clusters of 2 / 4 column neighbours (11.2 / 12.5-13.6 ms). The A operand rows are 16
+// floats = 64 bytes: SWIZZLE_64B.
 constexpr int KB_C = 8;                   // complex contraction elements per K-block (16 floats of A, 16 rows of B)
-constexpr int NRAW = 8;                   // slots of the raw ring (what TMA fills): decides how much load latency is covered
-constexpr int NCONV = 2;                  // slots of the converted ring (what the tensor core reads): conversion of K-block
-                                          // kb + 1 overlaps the MMAs of kb
+constexpr int NSTAGE = 4;
 constexpr uint32_t A_BYTES = TILE_M * 2 * KB_C * 4;   // 8 KiB  (128 rows x 16 floats)
 constexpr uint32_t BRAW_BYTES = 8 * KB_C * 128;   // 8 KiB  (8 groups x 8 rows x 128 B)
 constexpr uint32_t BCONV_BYTES = 8 * 2 * KB_C * 128;  // 16 KiB (8 groups x 16 rows x 128 B)
-constexpr uint32_t RAW_BYTES = A_BYTES + BRAW_BYTES;                 // 16 KiB: raw A tile, raw B tile
-constexpr uint32_t OFF_RAW_A = 0, OFF_RAW_B = A_BYTES;
-constexpr uint32_t CONV_BYTES = 2 * A_BYTES + 2 * BCONV_BYTES;       // 48 KiB: A hi, A lo, B hi, B lo
-constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_HI = 2 * A_BYTES, OFF_B_LO = 2 * A_BYTES + BCONV_BYTES;
-constexpr uint32_t OFF_RAW = 0, OFF_CONV = NRAW * RAW_BYTES;         // 128 KiB of raw slots, then 96 KiB of converted slots
-constexpr uint32_t OFF_BARS = OFF_CONV + NCONV * CONV_BYTES;
+constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_B_RAW = 2 * A_BYTES, OFF_B_HI = 2 * A_BYTES + BRAW_BYTES,
+                   OFF_B_LO = 2 * A_BYTES + BRAW_BYTES + BCONV_BYTES;
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + BRAW_BYTES + 2 * BCONV_BYTES;  // 56 KiB
+constexpr uint32_t OFF_BARS = NSTAGE * STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BARS + 256 + 1024;
 constexpr int NUM_CONVERTERS = 256;
 constexpr int NUM_THREADS = 128 + NUM_CONVERTERS;
@@ -83,8 +80,7 @@ __device__ __forceinline__ void drain_chunk(int c, uint32_t bar_accf, uint32_t b
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_acce + 8 * p);   // one arrival per warp (see the conversion loop)
+    mbar_arrive(bar_acce + 8 * p);
 }
 
 struct GemmArgs {
@@ -108,11 +104,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + OFF_BARS;
-    // barriers: raw_full[NRAW] (TMA bytes), raw_free[NRAW] (converters), conv_full[NCONV] (converters), conv_free[NCONV] (MMA
-    // commit), acc_full[2], acc_free[2]
-    const uint32_t bar_raw = bars, bar_rawfree = bars + 8 * NRAW, bar_conv = bars + 16 * NRAW, bar_empty = bar_conv + 8 * NCONV,
-                   bar_accf = bar_empty + 8 * NCONV, bar_acce = bar_accf + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 16 * NRAW + 16 * NCONV + 32);
+    const uint32_t bar_raw = bars, bar_conv = bars + 8 * NSTAGE, bar_empty = bars + 16 * NSTAGE, bar_accf = bars + 24 * NSTAGE,
+                   bar_acce = bars + 24 * NSTAGE + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BARS + 24 * NSTAGE + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = g.tiles_m * g.tiles_n;
@@ -128,17 +122,14 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int NC = (KB + CHUNK_KB - 1) / CHUNK_KB;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NRAW; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(bar_raw + 8 * s, 1);
-            mbar_init(bar_rawfree + 8 * s, NUM_CONVERTERS / 32);
-        }
-        for (int s = 0; s < NCONV; ++s) {
-            mbar_init(bar_conv + 8 * s, NUM_CONVERTERS / 32);
+            mbar_init(bar_conv + 8 * s, NUM_CONVERTERS);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int p = 0; p < 2; ++p) {
             mbar_init(bar_accf + 8 * p, 1);
-            mbar_init(bar_acce + 8 * p, NUM_CONVERTERS / 32);
+            mbar_init(bar_acce + 8 * p, NUM_CONVERTERS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -159,13 +150,13 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % NRAW;
-                const uint32_t use = kb / NRAW;
-                mbar_wait(bar_rawfree + 8 * s, (use & 1) ^ 1);
-                const uint32_t st = sbase + OFF_RAW + s * RAW_BYTES;
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
+                mbar_wait(bar_empty + 8 * s, (use & 1) ^ 1);
+                const uint32_t st = sbase + s * STAGE_BYTES;
                 mbar_arrive_expect_tx(bar_raw + 8 * s, A_BYTES + BRAW_BYTES);
-                tma_load_3d(st + OFF_RAW_A, &mapA, bar_raw + 8 * s, kb * 2 * KB_C, m0, b);
-                tma_load_4d(st + OFF_RAW_B, &mapB, bar_raw + 8 * s, 0, kb * KB_C, n0c * 2 / 32, b);
+                tma_load_3d(st + OFF_A_HI, &mapA, bar_raw + 8 * s, kb * 2 * KB_C, m0, b);
+                tma_load_4d(st + OFF_B_RAW, &mapB, bar_raw + 8 * s, 0, kb * KB_C, n0c * 2 / 32, b);
             }
         }
       } else if (warp == 1) {
@@ -174,8 +165,8 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             // D = f32, A = B = tf32, A K-major, B MN-major (bit 16), N = 256, M = 128
             const uint32_t idesc = idesc_tf32(128, 256, true);
             for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % NCONV;
-                const uint32_t use = kb / NCONV;
+                const int s = kb % NSTAGE;
+                const uint32_t use = kb / NSTAGE;
                 const int c = kb / CHUNK_KB, p = c & 1;
                 const bool first = (kb % CHUNK_KB) == 0;
                 if (first) {
@@ -184,7 +175,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
                 mbar_wait(bar_conv + 8 * s, use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = sbase + OFF_CONV + s * CONV_BYTES;
+                const uint32_t st = sbase + s * STAGE_BYTES;
                 const uint64_t a_hi = desc_kmajor_sw64(st + OFF_A_HI), a_lo = desc_kmajor_sw64(st + OFF_A_LO);
                 const uint32_t d = tmem_base + (uint32_t)p * 256u;
 #pragma unroll
@@ -240,8 +231,8 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const float* Sb = MODE == MODE_RECON ? g.S + (size_t)b * g.kmax : nullptr;
 
         for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % NRAW, cs = kb % NCONV;
-            const uint32_t use = kb / NRAW, cuse = kb / NCONV;
+            const int s = kb % NSTAGE;
+            const uint32_t use = kb / NSTAGE;
             float sc[NB];
             bool on[NB];
 #pragma unroll
@@ -251,12 +242,10 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 sc[i] = (MODE == MODE_RECON && on[i]) ? __ldg(Sb + cc) : 1.f;
             }
             mbar_wait(bar_raw + 8 * s, use & 1);
-            mbar_wait(bar_empty + 8 * cs, (cuse & 1) ^ 1);   // the MMAs that read this converted slot two K-blocks ago are done
-            const uint32_t rw = sbase + OFF_RAW + s * RAW_BYTES;
-            const uint32_t st = sbase + OFF_CONV + cs * CONV_BYTES;
+            const uint32_t st = sbase + s * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < NA; ++i) {
-                float4 av = lds128(rw + OFF_RAW_A + offA[i]);
+                float4 av = lds128(st + OFF_A_HI + offA[i]);
                 if (MODE == MODE_RECON) {
                     // columns of U at or beyond ranks[b] are not part of the product, whatever they hold (the last K-block
                     // may reach past the rank)
@@ -270,7 +259,7 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
-                float4 v = lds128(rw + OFF_RAW_B + offBraw[i]);
+                float4 v = lds128(st + OFF_B_RAW + offBraw[i]);
                 if (MODE == MODE_RECON) {
                     // modes beyond ranks[b] are never read as data, whatever they hold
                     v = on[i] ? make_float4(v.x * sc[i], v.y * sc[i], v.z * sc[i], v.w * sc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -283,16 +272,9 @@ cgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 sts128(st + OFF_B_HI + o1B[i], rot90(s0.hi));
                 sts128(st + OFF_B_LO + o1B[i], rot90(s0.lo));
             }
-            // one arrival per warp
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_conv + 8 * cs);
-                mbar_arrive(bar_rawfree + 8 * s);            // (the raw values are in registers or converted: refill it)
-            }
-            // promote the chunks whose MMAs have retired by now (every converter thread drains every chunk: the accumulators
-            // are split over all eight warps)
-            while (next_drain < NC && kb >= CHUNK_KB * (next_drain + 1) + DRAIN_LAG)
+            mbar_arrive(bar_conv + 8 * s);
+            if (kb >= CHUNK_KB + DRAIN_LAG && ((kb - DRAIN_LAG) % CHUNK_KB) == 0)
                 drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
         }
         while (next_drain < NC) drain_chunk(next_drain++, bar_accf, bar_acce, tmem_base, quad, chalf, acc);
