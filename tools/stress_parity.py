@@ -37,6 +37,8 @@ def main():
     rng = np.random.default_rng(seed)
     eng = get_engine(0)
     eng.set_option("eig_impl", eig_impl)
+    for kv in sys.argv[6:]:                              # further library options as name=value
+        eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     t0 = time.time()
     fails = 0
     for case in range(ncases):
