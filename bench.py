@@ -55,7 +55,7 @@ OPTIONS = {"small_jacobi": {"small_impl": 1}}   # library options a workload run
 # handles (host thread + stream each) that work through the cubes of a step concurrently: the eigen stage of one cube
 # (one CTA per matrix: 112 of 148 SMs at the KAT-7 shape, host polls in between) overlaps the other stages of the next
 HANDLES = {"kat7": 6, "meerkat": 1, "small": 6, "small_jacobi": 6}   # upper bound: never more than the rank's share of the host cores
-E2E_THREADS = int(os.environ.get("VISCO_E2E_THREADS", "0"))   # 0: six, or as many as the rank's share of the host cores allows
+E2E_THREADS = int(os.environ.get("VISCO_E2E_THREADS", "0"))   # 0: twelve, or as many as the rank's share of the host cores allows
 METRIC = "visibilities compressed+reconstructed /sec (GVis/s)"
 
 
@@ -520,8 +520,8 @@ def e2e_pipeline(Engine, torch, dist, dev, local, world, w, seconds=1.5):
     """e2e through the host-buffer C ABI: E2E_THREADS host threads, each with its own handle, stream and pinned buffers,
     each looping vk_compress_host -> vk_reconstruct_host on its own copy of the cube. Also one thread alone."""
     B, m, n, kw, kmax = w["B"], w["m"], w["n"], w["kw"], w["kmax"]
-    # measured on one GPU (KAT-7 cube): 2 threads 3.4, 3: 4.0, 4: 4.7, 6: 5.0, 8: 5.2 GVis/s (ceiling 5.9-6.0)
-    nthr = E2E_THREADS or max(2, min(6, len(os.sched_getaffinity(0)) // max(1, world)))
+    # measured on one GPU (KAT-7 cube): 2 threads 3.4, 3: 4.0, 4: 4.7, 6: 5.0, 8: 5.2, 12: 5.3 GVis/s (ceiling 5.9-6.0)
+    nthr = E2E_THREADS or max(2, min(12, len(os.sched_getaffinity(0)) // max(1, world)))
     per_mat = 8.0 * (2 * m * n + kmax * (m + n))
     Be = int(max(1, min(B, 6e9 // per_mat)))
 
