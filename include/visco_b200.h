@@ -81,7 +81,9 @@ int vk_sync(vk_handle h);
  *          SM count or three or more host threads are inside vk_compress_batched on this device, else one; 1 / 2 force
  *          one / two), "tridiag_nts" (rows of the trailing block that finish in shared memory, default 64),
  *          "tail_split" (0 = the remainder of a batch that is not a whole number of waves runs as its own sub-batch on a
- *          second stream, 1 = off),
+ *          second stream, 1 = off), "split_variant" (launch shape of the main sub-batch under that split, values as
+ *          "tridiag_variant"), "tridiag_pf" (min(m,n) = 512, two matrices per SM: tiles the L2 is asked for ahead of the
+ *          loads, default 1; 0 = none),
  *          "small_impl" (one-sided Jacobi on the matrix itself: 0 = for min(m,n) <= 32 when it fits one CTA, 1 = for every
  *          shape that fits (min(m,n) <= 64: BASELINE configs[3] as named), 2 = never),
  *          "factors_impl" (small ranks, wide matrices: 0 = one fused cluster kernel, 1 = the separate kernels),

@@ -462,6 +462,10 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->tridiag_impl = (int)v;
     else if (k == "tridiag_nts")
         h->tridiag_nts = (int)v;
+    else if (k == "tridiag_pf")
+        h->tridiag_pf = (int)v;
+    else if (k == "split_variant")
+        h->split_variant = (int)v;
     else if (k == "tail_split")
         h->tail_split = (int)v;
     else if (k == "factors_impl")

@@ -49,6 +49,8 @@ struct vk_context {
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t tail_ev[2] = {nullptr, nullptr};
     int tridiag_nts = -1;     // tridiag_sym.cu: largest trailing block that moves to shared memory (-1: whatever fits)
+    int tridiag_pf = 1;       // tridiag_sym.cu: L2 prefetch distance in tiles (r = 512, two matrices per SM; 0 = none)
+    int split_variant = 0;    // tridiag.cu: launch shape of the main sub-batch under the remainder split (as tridiag_variant)
     int32_t* bad = nullptr;   // per-matrix flags of the current vk_compress_batched call: Gram trace outside the safe range
     size_t bad_bytes = 0;     // (grow-only; bad[B] is the count)
     int recon_tc_impl = 0;   // 0 = persistent tcgen05 kernel for 8 < k <= 32 (recon_tc.cu), 1 = the older kernels

@@ -1961,7 +1961,9 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
             cudaStream_t main_st = h->stream;
             const int save_variant = h->tridiag_variant;
             h->in_split = true;
-            h->tridiag_variant = 1;   // one matrix per SM: B1 is a whole number of waves
+            // (round 2: one matrix per SM, B1 being a whole number of waves; with the L2 prefetch of the two-per-SM shape the
+            //  automatic choice wins: 183.3 -> 178.7 ms per compress of the MeerKAT shard; "split_variant" = 1 restores it)
+            h->tridiag_variant = h->split_variant;
             int rc = vk_launch_eigqr(h, W, B1, r, ld, scratch, sweeps_dev, done_dev, fixed_rank, decorrelation);
             if (!rc) {
                 unsigned char* sc2 = static_cast<unsigned char*>(scratch) + al(eig_layout(B1, r).total);

@@ -72,6 +72,9 @@ __device__ __forceinline__ void reduce_scatter(float2 (&t)[N], int lane) {
     }
 }
 
+// one 128-byte line into L2 (no register, no scoreboard entry): see the PF template parameter below
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct TileIt {
     int rho, I, K, Klast;   // serpentine round, row block, column chunk, chunk with the diagonal of the block
     bool valid;
@@ -81,10 +84,20 @@ struct TileIt {
 // SM so that one's barriers and scalar phases hide behind the other's pass - many matrices); DB: register double buffer
 // LDC: the row stride when it is known at compile time (0: use ld) - the eight loads of a tile then share one base
 // register pair and immediate offsets instead of a 64-bit add each
-template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC>
+// PF (r = 512, two matrices per SM, no register double buffer): the triangles of a wave do not fit the L2 (296 MB at the
+// start, and the first third of the steps requests 70 % of the bytes), so a tile load is a DRAM access the warp then waits
+// for. A warp asks the L2 for the tile it will load pfd tiles later - one prefetch instruction per tile, a lane per
+// 128-byte line - and, when its walk of step j is over, for the first tiles of its walk of step j + 1. Measured on the
+// MeerKAT shard (1040 matrices): 61.5 -> 54.5 ms with pfd = 1; 2: 55-59, 4: 55-60, 8: 67, 12: 70 ms (further ahead the
+// lines are gone again before they are used). The 512-thread shape already loads one tile ahead into registers and loses
+// with the extra instructions (63 -> 67-70 ms). Also measured, without effect on this kernel: L2 eviction-priority hints
+// (evict_last on the bottom rows of every triangle / on a fraction of the lines, evict_first on the rest) and a tile-major
+// copy of the triangle (a tile as TR * 256 contiguous bytes instead of TR pieces 4 KiB apart).
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC, bool PF = false>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     tridiag_symdefer_kernel(float2* __restrict__ Wall, int r, int ld_, size_t wstride, float* __restrict__ dall,
-                            float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts) {
+                            float* __restrict__ eall, float* __restrict__ tauall, float2* __restrict__ phall, int nts,
+                            int pfd) {
     constexpr int WD = EPL * 32;
     const int ld = LDC ? LDC : ld_;
     constexpr int SD_THREADS = NT, SD_WARPS = NT / 32;
@@ -242,13 +255,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             for (int k = e0 * 32 + lane; k < WD; k += 32) mypart[k] = make_float2(0.f, 0.f);
             float kl = 0.f;                              // per lane: 2 Re conj(v_i) rowpart_i - a_ii |v_i|^2 of the rows it met
 
-            auto first = [&]() {
+            // a warp's walk over the tiles of a step whose first live row block / column chunk are wb0 / we0 (wL blocks)
+            auto first_of = [&](int wb0, int we0, int wL) {
                 TileIt t;
-                t.rho = 0, t.I = b0 + warp, t.K = e0, t.valid = warp < L;
+                t.rho = 0, t.I = wb0 + warp, t.K = we0, t.valid = warp < wL;
                 t.Klast = (t.I * TR + TR - 1) >> 5;
                 return t;
             };
-            auto advance = [&](TileIt t) {
+            auto advance_of = [&](TileIt t, int wb0, int we0, int wL) {
                 if (t.K < t.Klast) {
                     ++t.K;
                     return t;
@@ -256,11 +270,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 ++t.rho;
                 const int u = t.rho * SD_WARPS + ((t.rho & 1) ? SD_WARPS - 1 - warp : warp);
                 // (u grows with the round, so the first block past the live range ends this warp's walk)
-                t.valid = u < L;
-                t.I = b0 + u;
-                t.K = e0;
+                t.valid = u < wL;
+                t.I = wb0 + u;
+                t.K = we0;
                 t.Klast = (t.I * TR + TR - 1) >> 5;
                 return t;
+            };
+            auto first = [&]() { return first_of(b0, e0, L); };
+            auto advance = [&](TileIt t) { return advance_of(t, b0, e0, L); };
+            auto prefetch = [&](const TileIt& t) {
+                if (lane < 2 * TR) prefetch_l2(M + (size_t)(t.I * TR + (lane >> 1)) * ld + t.K * 32 + (lane & 1) * 16);
             };
             auto load = [&](const TileIt& t, float2 (&x)[TR]) {
                 const int k = t.K * 32 + lane;
@@ -353,6 +372,15 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     for (int rr = 0; rr < TR; ++rr) racc[rr] = make_float2(0.f, 0.f);
                 }
             };
+            TileIt tp = first();                         // PF: the tile pfd loads ahead
+            if (PF)
+                for (int q = 0; q < pfd && tp.valid; ++q) tp = advance(tp);
+            auto ahead = [&]() {
+                if (PF && tp.valid) {
+                    prefetch(tp);
+                    tp = advance(tp);
+                }
+            };
             if (DB) {
                 float2 xa[TR], xb[TR];
                 TileIt t0 = first(), t1;
@@ -373,7 +401,17 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 float2 xa[TR];
                 for (TileIt t0 = first(); t0.valid; t0 = advance(t0)) {
                     load(t0, xa);
+                    ahead();
                     process(t0, xa);
+                }
+            }
+            if (PF && j + 3 < r) {
+                // the first tiles of this warp's walk of step j + 1
+                const int nb0 = (j + 2) / TR, ne0 = (j + 2) >> 5, nL = nblk - nb0;
+                TileIt tn = first_of(nb0, ne0, nL);
+                for (int q = 0; q < pfd && tn.valid; ++q) {
+                    prefetch(tn);
+                    tn = advance_of(tn, nb0, ne0, nL);
                 }
             }
             kacc = warp_sum(kl);
@@ -463,7 +501,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     }
 }
 
-template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC>
+template <int EPL, int TR, int NB, int NT, bool DB, bool RAGGED, int LDC, bool PF = false>
 int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d, float* e,
                     float* tau, float2* ph) {
     constexpr int WD = EPL * 32;
@@ -479,9 +517,9 @@ int launch_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int
     size_t tb = (size_t)nts * nts * sizeof(float2);
     if (tb < partb) tb = partb;
     const size_t smem = vec + tb;
-    auto kern = tridiag_symdefer_kernel<EPL, TR, NB, NT, DB, RAGGED, LDC>;
+    auto kern = tridiag_symdefer_kernel<EPL, TR, NB, NT, DB, RAGGED, LDC, PF>;
     VK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B, NT, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts);
+    kern<<<B, NT, smem, st>>>(W, r, ld, wstride, d, e, tau, ph, nts, h->tridiag_pf);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
 }
@@ -494,6 +532,8 @@ int launch_symdefer_r(vk_context* h, cudaStream_t st, float2* W, int B, int r, i
     const bool full = !ragged && ld == EPL * 32;   // the usual case: r = ld = 256 / 384 / 512
     if (variant == 1) {
         if (ragged) return launch_symdefer<EPL, 16, 6, 256, false, true, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
+        if (full && EPL == 16 && h->tridiag_pf > 0 && B > 2 * h->num_sms)   // more triangles than the L2 holds
+            return launch_symdefer<EPL, 16, 6, 256, false, false, EPL * 32, true>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
         if (full) return launch_symdefer<EPL, 16, 6, 256, false, false, EPL * 32>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
         return launch_symdefer<EPL, 16, 6, 256, false, false, 0>(h, st, W, B, r, ld, wstride, d, e, tau, ph);
     }
@@ -508,6 +548,8 @@ bool vk_tridiag_symdefer_supported(int r) { return r > 128 && r <= 512; }
 
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,
                                float* e, float* tau, float2* ph) {
+    // (three or four CTAs of 256 threads per SM with 8-row tiles, 80 / 64 registers: 1.35 / 1.7-1.8 ms per KAT-7 cube with
+    // 6 to 12 concurrent handles against 1.26 ms - the SMs are busy with two, what counts is the instruction count)
     // two matrices per SM once there are more matrices than SMs, or when three or more host threads are feeding this GPU
     // through their own handles (KAT-7 cube, 112 matrices: alone 1.58 vs 2.05 ms, but three concurrent handles reach 1.57
     // instead of 1.67 ms per cube because the cubes' kernels can share SMs); "tridiag_variant": 1 / 2 force one / two per SM
