@@ -10,6 +10,8 @@ eng.synth_fill(A, B // 4, 4)
 eng.set_option("eig_impl", 2)
 if len(sys.argv) > 4:
     eng.set_option("tridiag_impl", int(sys.argv[4]))
+for kv in sys.argv[5:]:                                   # further library options as name=value
+    eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
 for _ in range(2):
     eng.compress(A, compressionrank=8)
 torch.cuda.synchronize()
