@@ -13,6 +13,7 @@ LIB = os.path.join(HERE, "libvisco_b200.so")
 SOURCES = ["api.cu", "jacobi.cu", "stages.cu", "gram_tc.cu", "layout.cu", "cgemm_tc.cu", "topk.cu", "tridiag.cu", "recon_tc.cu",
            "tridiag_sym.cu", "tridiag_small.cu"]
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+CFLAGS += os.environ.get("VISCO_EXTRA_NVCC_FLAGS", "").split()   # development (e.g. -DVK_TRIDIAG_CLOCKS)
 LFLAGS = ["--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -30,6 +30,7 @@
 //   * once the trailing block fits into shared memory (next to the vectors; it overlays part[]) it moves there with
 //     everything pending applied and undeferred resident steps (as in kernel 1d of tridiag.cu) finish the reduction.
 #include <cmath>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -130,6 +131,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     int P = 0;  // pending pairs of the streaming phase (uniform)
     const int nblk = (r + TR - 1) / TR;
 
+#ifdef VK_TRIDIAG_CLOCKS
+    long long ck[6] = {0, 0, 0, 0, 0, 0}, c0 = clock64(), c1;
+#define VK_CK(i) do { c1 = clock64(); ck[i] += c1 - c0; c0 = c1; } while (0)
+#else
+#define VK_CK(i)
+#endif
     for (int j = 0; j + 2 < r; ++j) {
         const int e0 = (j + 1) >> 5;
         if (j0 < 0 && r - j <= nts) {
@@ -181,6 +188,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         ss = warp_sum(ss);
         if (lane == 0) s_part[warp] = ss;
         __syncthreads();
+        VK_CK(0);
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < SD_WARPS; ++w) tot += s_part[w];
@@ -207,6 +215,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             }
         }
         __syncthreads();
+        VK_CK(1);
         // the reflector replaces row j right of the diagonal (upper triangle: never read by the streaming passes)
         {
             float2* row = M + (size_t)j * ld;
@@ -420,8 +429,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             }
             kacc = warp_sum(kl);
         }
+        VK_CK(2);
         if (lane == 0) s_kpart[warp] = kacc;
         __syncthreads();
+        VK_CK(3);
         float kk = 0.f;
 #pragma unroll
         for (int w = 0; w < SD_WARPS; ++w) kk += s_kpart[w];
@@ -463,7 +474,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             P = upd ? 1 : P + 1;
         }
         __syncthreads();
+        VK_CK(4);
     }
+#ifdef VK_TRIDIAG_CLOCKS
+    if (tid % 32 == 0 && b == 0)
+        printf("[tridiag clocks] warp %d: row+norm %lld  scalar %lld  own pass %lld  barrier wait %lld  update %lld\n", warp, ck[0], ck[1],
+               ck[2], ck[3], ck[4]);
+#endif
     if (tid == 0) {
         if (r == 1) {
             d[0] = M[0].x;
@@ -553,7 +570,9 @@ bool vk_tridiag_symdefer_supported(int r) { return r > 128 && r <= 512; }
 int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B, int r, int ld, size_t wstride, float* d,
                                float* e, float* tau, float2* ph) {
     // (three or four CTAs of 256 threads per SM with 8-row tiles, 80 / 64 registers: 1.35 / 1.7-1.8 ms per KAT-7 cube with
-    // 6 to 12 concurrent handles against 1.26 ms - the SMs are busy with two, what counts is the instruction count)
+    // 6 to 12 concurrent handles against 1.26 ms; two per SM with 8-row tiles, which balance better (94 % against 80 %), with
+    // or without the register double buffer: 1.25-1.27 against 1.18 ms, MeerKAT shard compress 179-186 against 171 ms)
+    // (prefetch.global.L1 of the next tile at r = 256, two per SM: 1.22-1.24 against 1.18 ms)
     // two matrices per SM once there are more matrices than SMs, or when three or more host threads are feeding this GPU
     // through their own handles (KAT-7 cube, 112 matrices: alone 1.58 vs 2.05 ms, but three concurrent handles reach 1.57
     // instead of 1.67 ms per cube because the cubes' kernels can share SMs); "tridiag_variant": 1 / 2 force one / two per SM
