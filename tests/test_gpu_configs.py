@@ -264,6 +264,32 @@ def test_fused_factor_formation_matches_the_separate_kernels(eng, torch, m, n, k
         parity.check_factors(Ah[b], U0[b], S0[b], V0[b], k, compressionrank=k, label=f"fused factors {m}x{n} k{k} b={b}")
 
 
+@pytest.mark.parametrize("m,n,kw", [(64, 64, dict(compressionrank=8)), (64, 64, dict(decorrelation=0.95)), (48, 100, dict(decorrelation=0.9)),
+                                    (100, 48, dict(compressionrank=5)), (33, 200, dict(compressionrank=4)), (130, 40, dict())])
+def test_fused_small_gram_matches_the_separate_kernels(eng, torch, m, n, kw):
+    """gram_small_kernel (Gram product + trace normalisation of a matrix with min(m, n) <= 64 in one CTA, both sides:
+    rows for m <= n, columns for m > n; ragged extents, a contraction longer than one 64-step chunk) against the SIMT GEMM
+    + normalisation pass it replaces ("gram_small" = 1) and against the oracle."""
+    A = _device_cube(eng, torch, 10, 4, m, n)
+    res = {}
+    for impl in (1, 0):
+        eng.set_option("gram_small", impl)
+        try:
+            res[impl] = [x.clone() for x in eng.compress(A, **kw)]
+        finally:
+            eng.set_option("gram_small", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][3], res[1][3])                                     # ranks
+    S0, S1 = res[0][1], res[1][1]
+    assert float(((S0 - S1).abs() / S1.abs().clamp_min(1e-20)).max()) < 5e-6     # summation order differs
+    Ah = A.cpu().numpy()
+    U, S, Vt, ranks, stats = (x.cpu().numpy() for x in res[0])
+    assert np.all(stats[:, 3] == 1)
+    for b in (0, 1, 17, 39):
+        k = int(ranks[b])
+        parity.check_factors(Ah[b], U[b, :, :k], S[b, :k], Vt[b, :k], k, label=f"fused small gram {m}x{n} {kw} b={b}", **kw)
+
+
 def test_remainder_split_of_the_eigensolver_changes_nothing(eng, torch):
     """More matrices than SMs with a small remainder: the remainder runs as its own sub-batch on a second stream
     (tridiag.cu, "tail_split"). The split also switches the main sub-batch to the one-matrix-per-SM launch shape (other

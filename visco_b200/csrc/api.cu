@@ -170,6 +170,8 @@ int gram_stage(vk_context* h, const float2* A, int B, int m, int n, float2* W, f
         if (!vk_gram_tc_supported(m, n, side) || !aligned16)
             return vk_fail(h, VK_EINVAL, "gram_impl=2 (tcgen05) does not support this shape or alignment");
         if ((rc = vk_launch_gram_tc(h, A, B, m, n, W))) return rc;
+    } else if (h->gram_small == 0 && vk_gram_small_supported(m, n)) {
+        return vk_launch_gram_small(h, A, B, m, n, W, gscale, nonfinite, bad, nbad);   // normalisation included
     } else {
         if ((rc = vk_launch_gram_simt(h, A, B, m, n, side, W))) return rc;
     }
@@ -462,6 +464,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->tridiag_impl = (int)v;
     else if (k == "tridiag_nts")
         h->tridiag_nts = (int)v;
+    else if (k == "gram_small")
+        h->gram_small = (int)v;
     else if (k == "tridiag_pf")
         h->tridiag_pf = (int)v;
     else if (k == "split_variant")

@@ -49,6 +49,7 @@ struct vk_context {
     cudaStream_t tail_stream = nullptr;
     cudaEvent_t tail_ev[2] = {nullptr, nullptr};
     int tridiag_nts = -1;     // tridiag_sym.cu: largest trailing block that moves to shared memory (-1: whatever fits)
+    int gram_small = 0;       // min(m,n) <= 64: 0 = fused Gram + normalisation kernel, 1 = SIMT GEMM + normalisation pass
     int tridiag_pf = 1;       // tridiag_sym.cu: L2 prefetch distance in tiles (r = 512, two matrices per SM; 0 = none)
     int split_variant = 0;    // tridiag.cu: launch shape of the main sub-batch under the remainder split (as tridiag_variant)
     int32_t* bad = nullptr;   // per-matrix flags of the current vk_compress_batched call: Gram trace outside the safe range
@@ -151,6 +152,10 @@ int vk_launch_topk(vk_context* h, float2* W, int B, int r, int fixed_rank, int32
 
 int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int side, float2* W);
 int vk_launch_gram_tc(vk_context* h, const float2* A, int B, int m, int n, float2* W);
+// min(m, n) <= 64: Gram product and trace normalisation fused, one CTA per matrix (stages.cu)
+bool vk_gram_small_supported(int m, int n);
+int vk_launch_gram_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale_dev,
+                         int32_t* nonfinite_dev, int32_t* bad_dev, int32_t* nbad_dev);
 bool vk_gram_tc_supported(int m, int n, int side);
 
 // scale[b] = r / trace(W[b]) applied in place; gscale_dev[b] = trace/r ; nonfinite_dev[0] |= 1 when trace is NaN/Inf

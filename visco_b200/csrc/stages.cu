@@ -113,6 +113,124 @@ __global__ void __launch_bounds__(1024) gram_normalise_kernel(float2* __restrict
     }
 }
 
+// Gram product AND trace normalisation of a matrix with min(m, n) <= 64 in one CTA (BASELINE configs[3]: 8320 matrices of
+// 64 x 64). The general SIMT GEMM above spends its time in guarded element-wise operand loads and two barriers per 16
+// contraction steps, and the normalisation is a second pass over W. Here the r vectors (rows of A when m <= n, else columns)
+// sit in shared memory 64 contraction steps at a time (row stride 66: 128-bit reads of two steps, conflict-free over the
+// sixteen row classes), thread (ib, jb), ib <= jb, owns the 4 x 4 entries (ib + 16 p, jb + 16 q) - only the upper triangle of
+// blocks is computed, the mirror image is written as conjugates - and the finished matrix is staged in the same shared
+// memory for the trace and a coalesced, already scaled store. Same contract as vk_launch_gram_simt followed by
+// vk_launch_gram_normalise (reference: implicit in np.linalg.svd, compress_ms.py:350).
+template <bool SIDE1>
+__global__ void __launch_bounds__(160) gram_small_kernel(const float2* __restrict__ A, int m, int n, float2* __restrict__ W,
+                                                        float* __restrict__ gscale, int32_t* __restrict__ nonfinite,
+                                                        int32_t* __restrict__ bad, int32_t* __restrict__ nbad) {
+    constexpr int S = 66, NT = 160;
+    __shared__ __align__(16) float2 As[64 * S];
+    __shared__ float s_tr[2];
+    __shared__ float s_f;
+    const int r = SIDE1 ? n : m, K = SIDE1 ? m : n;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float2* Ab = A + (size_t)b * m * n;
+    int ib = 0, jb = 0;
+    {
+        int rem = tid;
+        while (ib < 16 && rem >= 16 - ib) rem -= 16 - ib, ++ib;
+        jb = ib + rem;
+    }
+    const bool worker = tid < 136;
+    float2 acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = make_float2(0.f, 0.f);
+    for (int k0 = 0; k0 < K; k0 += 64) {
+        for (int idx = tid; idx < 64 * 64; idx += NT) {
+            float2 v = make_float2(0.f, 0.f);
+            int i, kk;
+            if (!SIDE1) {
+                i = idx >> 6, kk = idx & 63;
+                if (i < m && k0 + kk < n) v = Ab[(size_t)i * n + k0 + kk];
+            } else {
+                kk = idx >> 6, i = idx & 63;
+                if (k0 + kk < m && i < n) v = Ab[(size_t)(k0 + kk) * n + i];
+            }
+            As[i * S + kk] = v;
+        }
+        __syncthreads();
+        if (worker) {
+            const float4* ap = reinterpret_cast<const float4*>(As + ib * S);
+            const float4* bp = reinterpret_cast<const float4*>(As + jb * S);
+#pragma unroll 4
+            for (int k2 = 0; k2 < 32; ++k2) {
+                float4 a[4], c[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = ap[p * 8 * S + k2], c[p] = bp[p * 8 * S + k2];   // (16 rows = 8 S float4)
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // conj(a) * c for both contraction steps
+                        acc[p][q].x = fmaf(a[p].x, c[q].x, fmaf(a[p].y, c[q].y, fmaf(a[p].z, c[q].z, fmaf(a[p].w, c[q].w, acc[p][q].x))));
+                        acc[p][q].y = fmaf(a[p].x, c[q].y, fmaf(-a[p].y, c[q].x, fmaf(a[p].z, c[q].w, fmaf(-a[p].w, c[q].z, acc[p][q].y))));
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    // the finished matrix, full storage, in shared memory: G[i][t] (side 1: the conjugate)
+    if (worker) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = ib + 16 * p, t = jb + 16 * q;
+                if (ib == jb && p > q) continue;         // (a diagonal class holds both (i, t) and (t, i): keep one)
+                float2 v = acc[p][q];
+                if (SIDE1) v.y = -v.y;
+                if (i == t) v.y = 0.f;
+                As[i * S + t] = v;
+                if (i != t) As[t * S + i] = make_float2(v.x, -v.y);   // exactly Hermitian
+            }
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float d = tid < r ? As[tid * S + tid].x : 0.f;
+        d = warp_sum(d);
+        if ((tid & 31) == 0) s_tr[tid >> 5] = d;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // (as gram_normalise_kernel)
+        const float tr = s_tr[0] + s_tr[1];
+        float g = tr / (float)r;
+        bool isbad = false;
+        if (!isfinite(g) || fabsf(g) < 1e-30f || fabsf(g) > 1e30f) {
+            if (bad) {
+                isbad = true;
+                bad[b] = 1;
+                atomicAdd(nbad, 1);
+            } else if (!isfinite(g)) {
+                atomicOr(nonfinite, 1);
+            }
+            g = 1.f;
+        }
+        if (!(g > 0.f)) g = 1.f;
+        gscale[b] = g;
+        s_f = isbad ? -1.f : 1.f / g;
+    }
+    __syncthreads();
+    const float f = s_f;
+    float2* Wb = W + (size_t)b * r * r;
+    for (int idx = tid; idx < r * r; idx += NT) {
+        const int i = idx / r, t = idx - i * r;
+        float2 v = As[i * S + t];
+        if (f < 0.f) v = make_float2(i == t ? 1.f : 0.f, 0.f);
+        else v.x *= f, v.y *= f;
+        Wb[idx] = v;
+    }
+}
+
 // Small path: vectors = rows of A (m <= n) or columns of A (m > n), normalised to unit rms norm, followed by e_i.
 __global__ void __launch_bounds__(256) pack_small_kernel(const float2* __restrict__ A, int m, int n,
                                                          float2* __restrict__ W, int ld, float* __restrict__ gscale,
@@ -924,6 +1042,16 @@ int vk_launch_gram_simt(vk_context* h, const float2* A, int B, int m, int n, int
     }
     GramOp1 op{A, W, m, n};
     return cgemm_launch<64, 64, 4, 4, 16>(h, op, B);
+}
+
+bool vk_gram_small_supported(int m, int n) { return (m < n ? m : n) <= 64; }
+
+int vk_launch_gram_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale_dev,
+                         int32_t* nonfinite_dev, int32_t* bad_dev, int32_t* nbad_dev) {
+    if (m <= n) gram_small_kernel<false><<<B, 160, 0, h->stream>>>(A, m, n, W, gscale_dev, nonfinite_dev, bad_dev, nbad_dev);
+    else gram_small_kernel<true><<<B, 160, 0, h->stream>>>(A, m, n, W, gscale_dev, nonfinite_dev, bad_dev, nbad_dev);
+    VK_LAUNCH_CHECK(h);
+    return VK_OK;
 }
 
 int vk_launch_gram_normalise(vk_context* h, float2* W, int B, int r, float* gscale_dev, int32_t* nonfinite_dev,
