@@ -86,6 +86,8 @@ int vk_sync(vk_handle h);
  *          loads, default 1; 0 = none),
  *          "small_impl" (one-sided Jacobi on the matrix itself: 0 = for min(m,n) <= 32 when it fits one CTA, 1 = for every
  *          shape that fits (min(m,n) <= 64: BASELINE configs[3] as named), 2 = never),
+ *          "tridiag_small_rs" (33 < min(m,n) <= 64: groups of two warps that share the rows of a matrix in the warp-level
+ *          tridiagonalisation, 1 / 2 / 4; 0 = two from 60 on),
  *          "gram_small" (min(m,n) <= 64 on the Gram path: 0 = Gram product and trace normalisation in one CTA per matrix,
  *          1 = the SIMT GEMM followed by the normalisation pass),
  *          "factors_impl" (small ranks, wide matrices: 0 = one fused cluster kernel, 1 = the separate kernels),

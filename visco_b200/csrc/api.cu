@@ -464,6 +464,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->tridiag_impl = (int)v;
     else if (k == "tridiag_nts")
         h->tridiag_nts = (int)v;
+    else if (k == "tridiag_small_rs")
+        h->tridiag_small_rs = (int)v;
     else if (k == "gram_small")
         h->gram_small = (int)v;
     else if (k == "tridiag_pf")

@@ -144,7 +144,17 @@ __global__ void __launch_bounds__(160) gram_small_kernel(const float2* __restric
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[p][q] = make_float2(0.f, 0.f);
+    // (rows of an even length from a 16-byte aligned base: two contraction steps per load)
+    const bool vec2 = !SIDE1 && (n & 1) == 0 && (reinterpret_cast<uintptr_t>(Ab) & 15) == 0;
     for (int k0 = 0; k0 < K; k0 += 64) {
+        if (vec2) {
+            for (int idx = tid; idx < 64 * 32; idx += NT) {
+                const int i = idx >> 5, kk = (idx & 31) * 2;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < m && k0 + kk < n) v = *reinterpret_cast<const float4*>(Ab + (size_t)i * n + k0 + kk);
+                *reinterpret_cast<float4*>(As + i * S + kk) = v;
+            }
+        } else
         for (int idx = tid; idx < 64 * 64; idx += NT) {
             float2 v = make_float2(0.f, 0.f);
             int i, kk;
@@ -222,6 +232,16 @@ __global__ void __launch_bounds__(160) gram_small_kernel(const float2* __restric
     __syncthreads();
     const float f = s_f;
     float2* Wb = W + (size_t)b * r * r;
+    if ((r & 1) == 0 && f >= 0.f && (reinterpret_cast<uintptr_t>(Wb) & 15) == 0) {
+        const int h2 = r >> 1;
+        for (int idx = tid; idx < r * h2; idx += NT) {
+            const int i = idx / h2, t = (idx - i * h2) * 2;
+            float4 v = *reinterpret_cast<const float4*>(As + i * S + t);
+            v.x *= f, v.y *= f, v.z *= f, v.w *= f;
+            *reinterpret_cast<float4*>(Wb + (size_t)i * r + t) = v;
+        }
+        return;
+    }
     for (int idx = tid; idx < r * r; idx += NT) {
         const int i = idx / r, t = idx - i * r;
         float2 v = As[i * S + t];
@@ -1075,7 +1095,8 @@ int vk_launch_select(vk_context* h, const float2* W, int B, int r, int ldot, int
     int P = 1;
     while (P < r) P <<= 1;
     const size_t smem = (size_t)P * 12;
-    select_kernel<<<B, 256, smem, h->stream>>>(W, r, ldot, ld, gscale_dev, mode_gram, fixed_rank, decorrelation, kmax,
+    // (r <= 64: 64 threads - the kernel is a latency chain per matrix, smaller CTAs put four times as many on an SM)
+    select_kernel<<<B, r <= 64 ? 64 : 256, smem, h->stream>>>(W, r, ldot, ld, gscale_dev, mode_gram, fixed_rank, decorrelation, kmax,
                                                perm_dev, inv_dev, S_dev, ranks_dev, stats_dev, sweeps_dev, done_dev);
     VK_LAUNCH_CHECK(h);
     return VK_OK;
