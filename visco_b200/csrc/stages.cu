@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(160) gram_small_kernel(const float2* __restric
         while (ib < 16 && rem >= 16 - ib) rem -= 16 - ib, ++ib;
         jb = ib + rem;
     }
-    const bool worker = tid < 136;
+    const bool worker = tid < 136 && ib < r && jb < r;   // (classes beyond r hold zero rows only)
     float2 acc[4][4];
 #pragma unroll
     for (int p = 0; p < 4; ++p)
@@ -1068,6 +1068,7 @@ bool vk_gram_small_supported(int m, int n) { return (m < n ? m : n) <= 64; }
 
 int vk_launch_gram_small(vk_context* h, const float2* A, int B, int m, int n, float2* W, float* gscale_dev,
                          int32_t* nonfinite_dev, int32_t* bad_dev, int32_t* nbad_dev) {
+    if (B <= 0) return VK_OK;
     if (m <= n) gram_small_kernel<false><<<B, 160, 0, h->stream>>>(A, m, n, W, gscale_dev, nonfinite_dev, bad_dev, nbad_dev);
     else gram_small_kernel<true><<<B, 160, 0, h->stream>>>(A, m, n, W, gscale_dev, nonfinite_dev, bad_dev, nbad_dev);
     VK_LAUNCH_CHECK(h);
