@@ -292,9 +292,9 @@ def test_fused_small_gram_matches_the_separate_kernels(eng, torch, m, n, kw):
 
 def test_remainder_split_of_the_eigensolver_changes_nothing(eng, torch):
     """More matrices than SMs with a small remainder: the remainder runs as its own sub-batch on a second stream
-    (tridiag.cu, "tail_split"). The split also switches the main sub-batch to the one-matrix-per-SM launch shape (other
-    tile height and deferral depth), so the two runs agree to rounding, not bit for bit; both are checked against the
-    oracle."""
+    (tridiag.cu, "tail_split"). The split may put the main sub-batch on the other launch shape of the tridiagonalisation
+    (tile height and deferral depth differ), so the two runs agree to rounding, not bit for bit; both are checked against
+    the oracle."""
     nsm = torch.cuda.get_device_properties(0).multi_processor_count
     B, m, n = nsm + 5, 160, 512
     A = _device_cube(eng, torch, B, 1, m, n)

@@ -572,7 +572,8 @@ int vk_launch_tridiag_symdefer(vk_context* h, cudaStream_t st, float2* W, int B,
     // (three or four CTAs of 256 threads per SM with 8-row tiles, 80 / 64 registers: 1.35 / 1.7-1.8 ms per KAT-7 cube with
     // 6 to 12 concurrent handles against 1.26 ms; two per SM with 8-row tiles, which balance better (94 % against 80 %), with
     // or without the register double buffer: 1.25-1.27 against 1.18 ms, MeerKAT shard compress 179-186 against 171 ms)
-    // (prefetch.global.L1 of the next tile at r = 256, two per SM: 1.22-1.24 against 1.18 ms)
+    // (prefetch.global.L1 of the next tile at r = 256, two per SM: 1.22-1.24 against 1.18 ms; deferral depth 4 / 6 / 8 of
+    // that shape: 1.19-1.22 / 1.18-1.19 / 1.18-1.19 ms per cube with six handles, 2.17 / 2.18 / 2.19 ms alone)
     // two matrices per SM once there are more matrices than SMs, or when three or more host threads are feeding this GPU
     // through their own handles (KAT-7 cube, 112 matrices: alone 1.58 vs 2.05 ms, but three concurrent handles reach 1.57
     // instead of 1.67 ms per cube because the cubes' kernels can share SMs); "tridiag_variant": 1 / 2 force one / two per SM
