@@ -88,6 +88,9 @@ int vk_sync(vk_handle h);
  *          shape that fits (min(m,n) <= 64: BASELINE configs[3] as named), 2 = never),
  *          "tridiag_small_rs" (33 < min(m,n) <= 64: groups of two warps that share the rows of a matrix in the warp-level
  *          tridiagonalisation, 1 / 2 / 4; 0 = two from 60 on),
+ *          "bisect_impl" (leading eigenvalues at a fixed small rank: 0 = batches of at least four matrices per SM with
+ *          min(m,n) <= 128 pack several matrices into a warp, one lane per eigenvalue; 1 = always one CTA per matrix with
+ *          eight lanes per eigenvalue),
  *          "gram_small" (min(m,n) <= 64 on the Gram path: 0 = Gram product and trace normalisation in one CTA per matrix,
  *          1 = the SIMT GEMM followed by the normalisation pass),
  *          "factors_impl" (small ranks, wide matrices: 0 = one fused cluster kernel, 1 = the separate kernels),

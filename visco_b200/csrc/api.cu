@@ -466,6 +466,8 @@ int vk_set_option(vk_handle h, const char* key, double v) {
         h->tridiag_nts = (int)v;
     else if (k == "tridiag_small_rs")
         h->tridiag_small_rs = (int)v;
+    else if (k == "bisect_impl")
+        h->bisect_impl = (int)v;
     else if (k == "gram_small")
         h->gram_small = (int)v;
     else if (k == "tridiag_pf")

@@ -50,6 +50,7 @@ struct vk_context {
     cudaEvent_t tail_ev[2] = {nullptr, nullptr};
     int tridiag_nts = -1;     // tridiag_sym.cu: largest trailing block that moves to shared memory (-1: whatever fits)
     int tridiag_small_rs = 0; // tridiag_small.cu: row groups per matrix for 33 < r <= 64 (1, 2 or 4; 0 = two from r = 60 on)
+    int bisect_impl = 0;      // leading eigenvalues of many small problems: 0 = packed kernel (several matrices per warp), 1 = one CTA each
     int gram_small = 0;       // min(m,n) <= 64: 0 = fused Gram + normalisation kernel, 1 = SIMT GEMM + normalisation pass
     int tridiag_pf = 1;       // tridiag_sym.cu: L2 prefetch distance in tiles (r = 512, two matrices per SM; 0 = none)
     int split_variant = 0;    // tridiag.cu: launch shape of the main sub-batch under the remainder split (as tridiag_variant)
