@@ -290,6 +290,34 @@ def test_fused_small_gram_matches_the_separate_kernels(eng, torch, m, n, kw):
         parity.check_factors(Ah[b], U[b, :, :k], S[b, :k], Vt[b, :k], k, label=f"fused small gram {m}x{n} {kw} b={b}", **kw)
 
 
+@pytest.mark.parametrize("m,n,k", [(64, 64, 8), (48, 70, 3), (100, 40, 15)])
+def test_packed_bisection_of_many_small_problems(eng, torch, m, n, k):
+    """bisect_packed_kernel (batches of at least four matrices per SM with min(m, n) <= 128 and a fixed rank <= 15: several
+    matrices per warp, one lane per eigenvalue) against the CTA-per-matrix kernel ("bisect_impl" = 1) and the oracle; the
+    batch is not a whole number of CTAs."""
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    nbl = nsm + 3
+    A = _device_cube(eng, torch, nbl, 4, m, n)
+    res = {}
+    for impl in (1, 0):
+        eng.set_option("bisect_impl", impl)
+        try:
+            res[impl] = [x.clone() for x in eng.compress(A, compressionrank=k)]
+        finally:
+            eng.set_option("bisect_impl", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(res[0][3], res[1][3])
+    S0, S1 = res[0][1], res[1][1]
+    assert float(((S0 - S1).abs() / S1.abs().clamp_min(1e-20)).max()) < 5e-6
+    Ah = A.cpu().numpy()
+    U, S, Vt, ranks, stats = (x.cpu().numpy() for x in res[0])
+    assert np.all(stats[:, 3] == 1)
+    B = A.shape[0]
+    for b in (0, 1, 2, 3, B // 2, B - 2, B - 1):
+        kk = int(ranks[b])
+        parity.check_factors(Ah[b], U[b, :, :kk], S[b, :kk], Vt[b, :kk], kk, compressionrank=k, label=f"packed bisection {m}x{n} k{k} b={b}")
+
+
 def test_remainder_split_of_the_eigensolver_changes_nothing(eng, torch):
     """More matrices than SMs with a small remainder: the remainder runs as its own sub-batch on a second stream
     (tridiag.cu, "tail_split"). The split may put the main sub-batch on the other launch shape of the tridiagonalisation
