@@ -290,7 +290,7 @@ def test_fused_small_gram_matches_the_separate_kernels(eng, torch, m, n, kw):
         parity.check_factors(Ah[b], U[b, :, :k], S[b, :k], Vt[b, :k], k, label=f"fused small gram {m}x{n} {kw} b={b}", **kw)
 
 
-@pytest.mark.parametrize("m,n,k", [(64, 64, 8), (48, 70, 3), (100, 40, 15)])
+@pytest.mark.parametrize("m,n,k", [(64, 64, 8), (48, 70, 3), (100, 40, 15), (128, 128, 1)])
 def test_packed_bisection_of_many_small_problems(eng, torch, m, n, k):
     """bisect_packed_kernel (batches of at least four matrices per SM with min(m, n) <= 128 and a fixed rank <= 15: several
     matrices per warp, one lane per eigenvalue) against the CTA-per-matrix kernel ("bisect_impl" = 1) and the oracle; the

@@ -1347,13 +1347,15 @@ __global__ void __launch_bounds__(8 * (TK_MAXK + 1) + 24) bisect_kernel(int r, i
 // by the instructions they issue (236 us; the three leading-pair kernels 0.80 -> 0.69 ms with this one). Here a warp takes 32 / nev matrices, one lane per eigenvalue, plain bisection until
 // the bracket cannot shrink; d and e^2 of the CTA's matrices sit in shared memory.
 constexpr int BP_WARPS = 4;
+// matrices per warp: as many as fit its lanes, at most eight (32 matrices per CTA: 32 KiB of shared memory at r = 128)
+__host__ __device__ inline int bp_group(int nev) { return 32 / nev < 8 ? 32 / nev : 8; }
 __global__ void __launch_bounds__(32 * BP_WARPS) bisect_packed_kernel(int B, int r, int nev, const float* __restrict__ dall,
                                                                       const float* __restrict__ eall,
                                                                       float* __restrict__ lamtop, int32_t* __restrict__ flag,
                                                                       float gap) {
     extern __shared__ float bs_sm[];   // [matrices of the CTA][2 r]: d, e^2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = 32 / nev, mpc = G * BP_WARPS;
+    const int G = bp_group(nev), mpc = G * BP_WARPS;
     const int b0 = blockIdx.x * mpc;
     for (int idx = tid; idx < mpc * r; idx += 32 * BP_WARPS) {
         const int ml = idx / r, i = idx - ml * r, b = b0 + ml;
@@ -2092,7 +2094,7 @@ int vk_launch_eigqr(vk_context* h, float2* W, int B, int r, int ld, void* scratc
         int32_t* flag = reinterpret_cast<int32_t*>(sc + L.flag);
         if (h->bisect_impl != 1 && B >= 4 * h->num_sms && k + 1 <= 16 && r <= 128) {
             // many small problems: several matrices per warp, one lane per eigenvalue
-            const int mpc = (32 / (k + 1)) * BP_WARPS;
+            const int mpc = bp_group(k + 1) * BP_WARPS;
             bisect_packed_kernel<<<(B + mpc - 1) / mpc, 32 * BP_WARPS, (size_t)mpc * 2 * r * 4, st>>>(B, r, k + 1, d, e, lamtop,
                                                                                                    flag, TK_GAP);
         } else {
