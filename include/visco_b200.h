@@ -94,7 +94,10 @@ int vk_sync(vk_handle h);
  *          "gram_small" (min(m,n) <= 64 on the Gram path: 0 = Gram product and trace normalisation in one CTA per matrix,
  *          1 = the SIMT GEMM followed by the normalisation pass),
  *          "factors_impl" (small ranks, wide matrices: 0 = one fused cluster kernel, 1 = the separate kernels),
- *          "recon_tc_impl" (8 < k <= 32: 0 = persistent tcgen05 kernel with bulk tensor stores, 1 = the older kernels).
+ *          "recon_tc_impl" (8 < k <= 32: 0 = persistent tcgen05 kernel with bulk tensor stores, 1 = the older kernels),
+ *          "recon_generic" / "jacobi_generic" (comparison runs: 1 = the generic SIMT GEMM for every reconstruction and factor
+ *          formation / the global-memory Jacobi kernels for every size; "jacobi_generic" = 2 also takes the round-1
+ *          full-storage tridiagonalisation for 256 < min(m,n) <= 512).
  *          Every choice of these leaves the results within the tolerances of DESIGN.md section 2. */
 int vk_set_option(vk_handle h, const char* key, double value);
 /* bytes of device workspace vk_compress_batched needs for this problem (it allocates/grows the handle's own

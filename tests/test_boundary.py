@@ -62,3 +62,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no CPU fallback", ""), f"{f} mentions the oracle"
+
+
+def test_every_library_option_is_documented_in_the_header():
+    """vk_set_option's table (csrc/api.cu) and the option list in include/visco_b200.h must not drift apart."""
+    import re
+    api = open(os.path.join(ROOT, "visco_b200", "csrc", "api.cu")).read()
+    hdr = open(os.path.join(ROOT, "include", "visco_b200.h")).read()
+    opts = re.findall(r'k == "([a-z0-9_]+)"', api)
+    assert len(opts) >= 30 and len(set(opts)) == len(opts)
+    missing = [o for o in opts if f'"{o}"' not in hdr]
+    assert not missing, f"options not described in include/visco_b200.h: {missing}"
