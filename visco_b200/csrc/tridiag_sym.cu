@@ -243,19 +243,21 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 if (lane == 0) pv[i] = acc;
             }
         } else {
-            if (!upd && warp < P) {
-                // alpha_s = w_s^H v, beta_s = v_s^H v for the pending pair s = warp
+            // alpha_s = w_s^H v, beta_s = v_s^H v of pending pair s: one warp each, taken from the end of the warp order that
+            // gets no block in the last (incomplete) round of the walk below (same arithmetic whichever warp does it)
+            const int ps = ((((nblk - (j + 1) / TR) - 1) / SD_WARPS) & 1) ? warp : SD_WARPS - 1 - warp;
+            if (!upd && ps < P) {
                 float2 aa = make_float2(0.f, 0.f), bb = make_float2(0.f, 0.f);
                 for (int k = j + 1 + lane; k < r; k += 32) {
                     const float2 v = vnew[k];
-                    const float4 c = VW[warp * WD + k];
+                    const float4 c = VW[ps * WD + k];
                     aa.x = fmaf(c.z, v.x, fmaf(c.w, v.y, aa.x));
                     aa.y = fmaf(c.z, v.y, fmaf(-c.w, v.x, aa.y));
                     bb.x = fmaf(c.x, v.x, fmaf(c.y, v.y, bb.x));
                     bb.y = fmaf(c.x, v.y, fmaf(-c.y, v.x, bb.y));
                 }
                 aa.x = warp_sum(aa.x), aa.y = warp_sum(aa.y), bb.x = warp_sum(bb.x), bb.y = warp_sum(bb.y);
-                if (lane == 0) s_ab[warp] = aa, s_ab[NB + warp] = bb;
+                if (lane == 0) s_ab[ps] = aa, s_ab[NB + ps] = bb;
             }
             const int jl = (j + 1) & 31;                 // lane that holds column j+1 (in chunk e0)
             const int b0 = (j + 1) / TR;                 // first row block with a live row
